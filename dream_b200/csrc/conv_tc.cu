@@ -1,0 +1,455 @@
+// conv_tc.cu -- im2col-free implicit-GEMM convolution on the sm_100a tensor cores.
+//
+// One kernel covers every conv / deconv-phase / 1x1 layer of the DREAM networks
+// (reference: dream/models.py:591-747 vgg path, :22-136 resnet path).  A convolution is
+// evaluated as   Y[p, co] = sum_tap sum_ci X[p*stride + (dy,dx)_tap, ci] * Wt[tap][co][ci]
+// i.e. a sum over "taps" of shifted 1x1 GEMMs:
+//   * A operand  : a (tw x th) patch of output pixels -> tw*th <= 128 rows of 64 input channels,
+//                  fetched by ONE 4-D TMA box per (tap, channel chunk) straight from the NHWC
+//                  activation; the tap shift is a coordinate offset and the zero padding is the
+//                  TMA out-of-bounds fill, so no im2col buffer ever exists.
+//   * B operand  : weights [tap][Cout][Cin] fp16, a 3-D TMA box of BLOCK_N x 64.
+//   * D          : fp32 accumulator in TMEM (128 lanes x BLOCK_N columns), double buffered so the
+//                  epilogue of tile i overlaps the MMAs of tile i+1.
+//   * epilogue   : tcgen05.ld -> +bias (+residual) (ReLU) -> fp16 -> 128B-swizzled smem -> TMA store
+//                  (the store box clips partial tiles), or fp32 NCHW for the network head.
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer + TMEM owner, warps2-5 = epilogue.
+// Persistent: grid = #SMs, tiles round-robin.
+#include "common.cuh"
+#include "dreamb200.h"
+
+#include <mutex>
+
+namespace db200 {
+
+struct ConvParams {
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int tw, th;
+  int B, Ho, Wo;
+  int in_stride;
+  int taps, kchunks;
+  int8_t dy[DREAMB200_MAX_TAPS], dx[DREAMB200_MAX_TAPS];
+  const float* bias;
+  const __half* residual;
+  int Cout_pad;
+  int relu;
+  float* out_f32;
+  int cout_real;
+  int stages;
+};
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 fp16
+constexpr int kStageOutBytes = 128 * 128;
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BLOCK_N, int OUT_MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                            : (2 * BLOCK_N <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int stages = p.stages;
+  const uint32_t smem_ab = smem_base;                                   // stages * kStageBytes
+  const uint32_t smem_out = smem_ab + stages * kStageBytes;             // 2 * 16 KB (NHWC mode)
+  const uint32_t out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes : 0;
+  const uint32_t bar_base = smem_out + out_bytes;                       // barriers (8 B each)
+  // full[s], empty[s], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (OUT_MODE == DREAMB200_OUT_NHWC_F16) tma_prefetch_desc(&tmC);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int num_kb = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n = tile % p.n_tiles;
+        int t = tile / p.n_tiles;
+        int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        int ty = t % p.tiles_y;
+        int b = t / p.tiles_y;
+        const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int xi = x0 + p.dx[tap], yi = y0 + p.dy[tap];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_ab + stage * kStageBytes;
+            mbar_expect_tx(full_bar(stage), (uint32_t)(p.tw * p.th * 128 + kBBytes));
+            tma_load_4d(sa, &tmA, full_bar(stage), kc * 64, xi, yi, b);
+            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), kc * 64, n * BLOCK_N, tap);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_ab + stage * kStageBytes;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+            umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // accumulator row == output pixel inside the tile
+    const int epi_tid = threadIdx.x - 64;
+    const int ly = row / p.tw, lx = row - ly * p.tw;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      int tx = t % p.tiles_x;
+      t /= p.tiles_x;
+      int ty = t % p.tiles_y;
+      int b = t / p.tiles_y;
+      const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
+      const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+
+      if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
+        const __half* res_row = nullptr;
+        if (p.residual != nullptr && valid)
+          res_row = p.residual + ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
+          const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
+          if (epi_tid == 0) tma_store_wait_read<1>();   // the store that used obuf has read it
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
+            tmem_wait_ld();
+            const int ch0 = n * BLOCK_N + c * 64 + h * 32;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
+            }
+            if (res_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64 + h * 32 + i));
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 rf = __half22float2(rh[j]);
+                  f[i + 2 * j] += rf.x;
+                  f[i + 2 * j + 1] += rf.y;
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w0 = pack_h2(f[8 * j + 0], f[8 * j + 1]);
+              const uint32_t w1 = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+              const uint32_t w2 = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+              const uint32_t w3 = pack_h2(f[8 * j + 6], f[8 * j + 7]);
+              const uint32_t chunk16 = (uint32_t)(h * 4 + j) ^ (uint32_t)(row & 7);
+              const uint32_t dst = obuf + (uint32_t)row * 128u + chunk16 * 16u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1),
+                           "r"(w2), "r"(w3)
+                           : "memory");
+            }
+          }
+          if (c == BLOCK_N / 64 - 1) {
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (epi_tid == 0) {
+            tma_store_4d(&tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
+            tma_store_commit();
+          }
+        }
+      } else {
+        // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (valid) {
+          const size_t plane = (size_t)p.Ho * p.Wo;
+          float* o = p.out_f32 + (size_t)b * p.cout_real * plane + (size_t)oy * p.Wo + ox;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (k < p.cout_real) {
+              float f = __uint_as_float(v[k]) + (p.bias != nullptr ? __ldg(p.bias + k) : 0.0f);
+              if (p.relu) f = fmaxf(f, 0.0f);
+              o[(size_t)k * plane] = f;
+            }
+          }
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+    if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && epi_tid == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                    const uint32_t* estride, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+// Pick the output patch (tw x th <= 128 pixels) that wastes the fewest accumulator rows.
+// `even` forces even patch sides (needed when a 2x2 pool is fused on top of the patch).
+static void choose_tile(int Wo, int Ho, int in_stride, int* tw_out, int* th_out) {
+  double best = -1.0;
+  int btw = 1, bth = 1;
+  const int max_side = 256 / in_stride;  // TMA box side limit (in input elements)
+  for (int tw = 1; tw <= 128 && tw <= Wo && tw <= max_side; ++tw) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th > max_side) th = max_side;
+    const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    const double util = (double)Wo * Ho / (double)(tiles * 128);
+    // on ties prefer the wider patch (longer contiguous runs per TMA row)
+    if (util > best + 1e-9 || (util > best - 1e-9 && tw > btw)) {
+      best = util;
+      btw = tw;
+      bth = th;
+    }
+  }
+  *tw_out = btw;
+  *th_out = bth;
+}
+
+template <int BLOCK_N, int OUT_MODE>
+static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  choose_tile(d->Wo, d->Ho, d->in_stride, &p.tw, &p.th);
+  p.tiles_x = (d->Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (d->Ho + p.th - 1) / p.th;
+  p.n_tiles = d->Cout_pad / BLOCK_N;
+  p.B = d->B;
+  p.Ho = d->Ho;
+  p.Wo = d->Wo;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * d->B;
+  p.in_stride = d->in_stride;
+  p.taps = d->taps;
+  p.kchunks = d->Cin / 64;
+  memcpy(p.dy, d->tap_dy, sizeof(p.dy));
+  memcpy(p.dx, d->tap_dx, sizeof(p.dx));
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.Cout_pad = d->Cout_pad;
+  p.relu = d->relu;
+  p.out_f32 = (OUT_MODE == DREAMB200_OUT_NCHW_F32) ? reinterpret_cast<float*>(d->y) : nullptr;
+  p.cout_real = d->cout_real;
+
+  constexpr int kStageBytes = kABytes + BLOCK_N * 128;
+  const int out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes : 0;
+  const int budget = 232448 - 1024 - out_bytes - 512;
+  int stages = budget / kStageBytes;
+  if (stages > 8) stages = 8;
+  DB_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 stages");
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * kStageBytes + out_bytes + 512;
+
+  // A: activation NHWC (C, W, H, B); box (64, tw, th, 1); element stride = conv stride
+  CUtensorMap tmA, tmB, tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+    const uint32_t s = (uint32_t)d->in_stride;
+    uint32_t box[4] = {64, (uint32_t)p.tw * s, (uint32_t)p.th * s, 1};
+    uint32_t es[4] = {1, s, s, 1};
+    DB_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv: TMA box too large (%u x %u)", box[1], box[2]);
+    if (make_map(&tmA, d->x, 4, dims, str, box, es, "activation")) return -1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->taps};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {64, (uint32_t)BLOCK_N, 1};
+    uint32_t es[3] = {1, 1, 1};
+    if (make_map(&tmB, d->w, 3, dims, str, box, es, "weights")) return -1;
+  }
+  if (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
+    uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_map(&tmC, d->y, 4, dims, str, box, es, "output")) return -1;
+  }
+
+  auto kern = conv_tc_kernel<BLOCK_N, OUT_MODE>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, p);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  DB_REQUIRE(d != nullptr, "conv: null descriptor");
+  DB_REQUIRE(d->x && d->w && d->y, "conv: null tensor pointer");
+  DB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "conv: Cin=%d must be a positive multiple of 64", d->Cin);
+  DB_REQUIRE(d->taps >= 1 && d->taps <= DREAMB200_MAX_TAPS, "conv: taps=%d out of range", d->taps);
+  DB_REQUIRE(d->in_stride == 1 || d->in_stride == 2, "conv: stride %d unsupported", d->in_stride);
+  DB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "conv: empty tensor");
+  DB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0,
+             "conv: tensors must be 16-byte aligned");
+  const int sms = sm_count();
+  if (d->out_mode == DREAMB200_OUT_NCHW_F32) {
+    DB_REQUIRE(d->Cout_pad == 16, "conv: NCHW_F32 head needs Cout_pad == 16 (got %d)", d->Cout_pad);
+    DB_REQUIRE(d->cout_real >= 1 && d->cout_real <= 16, "conv: cout_real=%d out of range", d->cout_real);
+    DB_REQUIRE(d->residual == nullptr, "conv: residual unsupported for the NCHW_F32 head");
+    return launch<16, DREAMB200_OUT_NCHW_F32>(d, stream, sms);
+  }
+  DB_REQUIRE(d->out_mode == DREAMB200_OUT_NHWC_F16, "conv: unknown out_mode %d", d->out_mode);
+  DB_REQUIRE(d->Cout_pad > 0 && d->Cout_pad % 64 == 0, "conv: Cout_pad=%d must be a multiple of 64",
+             d->Cout_pad);
+  DB_REQUIRE((d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0,
+             "conv: output strides must be multiples of 16 bytes");
+  if (d->Cout_pad % 256 == 0) return launch<256, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
+  if (d->Cout_pad % 128 == 0) return launch<128, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
+  return launch<64, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
+}

@@ -1,0 +1,159 @@
+"""Torch-tensor wrappers over the C-ABI (include/dreamb200.h).
+
+Tensors are only carriers of device memory here: every op hands raw pointers and the
+current CUDA stream to libdreamb200.so.  Activations are NHWC fp16 (`[B,H,W,C]`, C % 64 == 0).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
+              y_strides=None, head_cout=None):
+    """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
+
+    x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
+    taps: list of (dy,dx) input offsets.  Returns y [B,Ho,Wo,Cout_pad] fp16, or when
+    `head_cout` is given a fp32 NCHW [B,head_cout,Ho,Wo] tensor (Cout_pad must be 16).
+    `y`/`y_strides` (w,h,b element strides) let a deconv phase write an interleaved view.
+    """
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4
+    assert w.dtype == torch.float16 and w.is_contiguous() and w.dim() == 3
+    B, H, W_, Cin = x.shape
+    T, Cout_pad, Cin_w = w.shape
+    assert Cin_w == Cin and T == len(taps), (w.shape, x.shape, len(taps))
+    d = ConvDesc()
+    d.x = x.data_ptr(); d.B = B; d.H = H; d.W = W_; d.Cin = Cin; d.in_stride = stride
+    d.w = w.data_ptr(); d.bias = bias.data_ptr() if bias is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= Cout_pad and bias.is_cuda
+    d.taps = T; d.Cout_pad = Cout_pad
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i] = dy; d.tap_dx[i] = dx
+    d.Ho = Ho; d.Wo = Wo
+    if head_cout is not None:
+        if y is None:
+            y = torch.empty((B, head_cout, Ho, Wo), dtype=torch.float32, device=x.device)
+        assert y.dtype == torch.float32 and y.is_contiguous()
+        d.out_mode = _lib.OUT_NCHW_F32; d.cout_real = head_cout
+        d.y_stride_w = 1; d.y_stride_h = Wo; d.y_stride_b = head_cout * Ho * Wo
+    else:
+        if y is None:
+            y = torch.empty((B, Ho, Wo, Cout_pad), dtype=torch.float16, device=x.device)
+            y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
+        elif y_strides is None:
+            assert y.is_contiguous() and tuple(y.shape) == (B, Ho, Wo, Cout_pad)
+            y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
+        d.out_mode = _lib.OUT_NHWC_F16; d.cout_real = Cout_pad
+        d.y_stride_w, d.y_stride_h, d.y_stride_b = y_strides
+    d.y = y.data_ptr() if not isinstance(y, int) else y
+    if residual is not None:
+        assert residual.dtype == torch.float16 and residual.is_contiguous()
+        assert tuple(residual.shape) == (B, Ho, Wo, Cout_pad)
+        d.residual = residual.data_ptr()
+    d.relu = 1 if relu else 0
+    check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
+    return y
+
+
+def im2col_first(x, R, S, stride, pad, Kpad):
+    """fp32 NCHW [B,3,H,W] -> fp16 NHWC patches [B,Ho,Wo,Kpad] (k = (r*S+s)*3+c)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+    B, _, H, W_ = x.shape
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W_ + 2 * pad - S) // stride + 1
+    out = torch.empty((B, Ho, Wo, Kpad), dtype=torch.float16, device=x.device)
+    check(lib().dreamb200_im2col_first(_ptr(x), _ptr(out), B, H, W_, R, S, stride, pad, Ho, Wo, Kpad,
+                                       _stream()), "dreamb200_im2col_first")
+    return out
+
+
+def maxpool(x, k, s, p):
+    B, H, W_, Cc = x.shape
+    Ho = (H + 2 * p - k) // s + 1
+    Wo = (W_ + 2 * p - k) // s + 1
+    y = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
+    check(lib().dreamb200_maxpool_nhwc(_ptr(x), _ptr(y), B, H, W_, Cc, k, s, p, Ho, Wo, _stream()),
+          "dreamb200_maxpool_nhwc")
+    return y
+
+
+def upsample2(x):
+    B, H, W_, Cc = x.shape
+    y = torch.empty((B, 2 * H, 2 * W_, Cc), dtype=torch.float16, device=x.device)
+    check(lib().dreamb200_upsample2_nhwc(_ptr(x), _ptr(y), B, H, W_, Cc, _stream()), "dreamb200_upsample2_nhwc")
+    return y
+
+
+def nhwc_to_nchw_f32(x, C_real):
+    B, H, W_, Cpad = x.shape
+    y = torch.empty((B, C_real, H, W_), dtype=torch.float32, device=x.device)
+    check(lib().dreamb200_nhwc_f16_to_nchw_f32(_ptr(x), _ptr(y), B, H, W_, Cpad, C_real, _stream()),
+          "dreamb200_nhwc_f16_to_nchw_f32")
+    return y
+
+
+def nchw_to_nhwc_f16(x, Cpad):
+    B, Cc, H, W_ = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty((B, H, W_, Cpad), dtype=torch.float16, device=x.device)
+    check(lib().dreamb200_nchw_f32_to_nhwc_f16(_ptr(x), _ptr(y), B, H, W_, Cc, Cpad, _stream()),
+          "dreamb200_nchw_f32_to_nhwc_f16")
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (load time / once per optimizer step; plain torch ops, not on the hot path)
+# ----------------------------------------------------------------------------------------------
+TAPS_3x3 = [(r - 1, s - 1) for r in range(3) for s in range(3)]
+
+
+def pack_conv_weight(w, rs_list, cin_pad=None, cout_pad=None, scale=None):
+    """OIHW fp32 conv weight -> fp16 [taps, Cout_pad, Cin_pad]; rs_list selects (r,s) per tap.
+    `scale` (per-Cout fp32) folds an eval-mode BatchNorm into the weights."""
+    Cout, Cin, R, S = w.shape
+    cin_pad = cin_pad or round_up(Cin, 64)
+    cout_pad = cout_pad or round_up(Cout, 64)
+    wf = w.detach().float()
+    if scale is not None:
+        wf = wf * scale.view(-1, 1, 1, 1)
+    out = torch.zeros((len(rs_list), cout_pad, cin_pad), dtype=torch.float16, device=w.device)
+    for t, (r, s) in enumerate(rs_list):
+        out[t, :Cout, :Cin] = wf[:, :, r, s].to(torch.float16)
+    return out.contiguous()
+
+
+def pack_first_weight(w, Kpad, cout_pad=None, scale=None):
+    """First-layer weight [Cout,3,R,S] -> [1, Cout_pad, Kpad] matching im2col_first's k order."""
+    Cout, Cin, R, S = w.shape
+    assert Cin == 3
+    cout_pad = cout_pad or round_up(Cout, 64)
+    wf = w.detach().float()
+    if scale is not None:
+        wf = wf * scale.view(-1, 1, 1, 1)
+    flat = wf.permute(0, 2, 3, 1).reshape(Cout, R * S * 3)   # k = (r*S+s)*3 + c
+    out = torch.zeros((1, cout_pad, Kpad), dtype=torch.float16, device=w.device)
+    out[0, :Cout, :R * S * 3] = flat.to(torch.float16)
+    return out.contiguous()
+
+
+def pad_bias(b, cout_pad, device):
+    out = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
+    if b is not None:
+        out[: b.numel()] = b.detach().float()
+    return out

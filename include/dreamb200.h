@@ -1,0 +1,89 @@
+/*
+ * dreamb200.h -- C-ABI of the B200-native DREAM hot path (libdreamb200.so).
+ *
+ * Every entry point replaces a torch/cuDNN/scipy library call made by the
+ * reference on its belief-map path.  Citations are into NVlabs/DREAM:
+ *
+ *   dreamb200_conv2d_fwd        nn.Conv2d / nn.ConvTranspose2d (+bias +BN-fold +ReLU +residual)
+ *                               dream/models.py:591-615,690-747 (vgg trunk/decoder/heads),
+ *                               :22-32,:37-136 (resnet trunk + deconv head)
+ *   dreamb200_im2col_first      first-layer patch gather feeding conv2d_fwd
+ *                               (models.py:591-599 3x3 p1; torchvision resnet conv1 7x7 s2 p3, models.py:23)
+ *   dreamb200_maxpool_nhwc      nn.MaxPool2d(2) models.py:589 ; resnet maxpool k3 s2 p1 models.py:27
+ *   dreamb200_upsample2_nhwc    nn.Upsample(scale_factor=2) (nearest) models.py:691,703
+ *   dreamb200_peaks             dream/image_proc.py:914-1018 peaks_from_belief_maps
+ *                               + top-2 bookkeeping for dream/network.py:548-577
+ *   dreamb200_softargmax        dream/spatial_softmax.py:24-95 SoftArgmaxPavlo.forward
+ *   backward entry points       autograd of the same ops (network.py:328-338 loss.backward())
+ *
+ * Conventions: raw device pointers, plain ints, an explicit cudaStream_t (passed as
+ * void*), int return (0 = ok, <0 = error; text via dreamb200_last_error()).  No
+ * allocation, no torch types, no exceptions.  Activations are NHWC fp16 with the
+ * channel count padded to a multiple of 64; weights are fp16 [tap][Cout_pad][Cin_pad].
+ */
+#ifndef DREAMB200_H_
+#define DREAMB200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DREAMB200_MAX_TAPS 16
+
+/* output modes of conv2d_fwd */
+#define DREAMB200_OUT_NHWC_F16 0   /* fp16 NHWC through TMA store (strided view allowed) */
+#define DREAMB200_OUT_NCHW_F32 1   /* fp32 NCHW, first cout_real channels (network head)  */
+
+typedef struct dreamb200_conv_desc {
+  /* input activation, NHWC fp16, dense */
+  const void* x; int32_t B, H, W, Cin;      /* Cin % 64 == 0 */
+  int32_t in_stride;                        /* spatial stride of the conv (1 or 2) */
+  /* weights fp16 [taps][Cout_pad][Cin], bias fp32 [Cout_pad] (may be NULL) */
+  const void* w; const float* bias;
+  int32_t taps; int32_t Cout_pad;           /* Cout_pad % 64 == 0, or 16 for the NCHW_F32 head */
+  int8_t tap_dy[DREAMB200_MAX_TAPS];        /* input offset of each tap, in input pixels   */
+  int8_t tap_dx[DREAMB200_MAX_TAPS];
+  /* output: logical size Ho x Wo; element strides let a deconv phase write an
+     interleaved view of a larger tensor (y points at the phase's first pixel). */
+  void* y; int32_t Ho, Wo;
+  int64_t y_stride_w, y_stride_h, y_stride_b;   /* in elements of the output dtype */
+  int32_t out_mode; int32_t cout_real;      /* cout_real only for NCHW_F32 */
+  /* fused epilogue */
+  const void* residual;                     /* fp16 NHWC [B,Ho,Wo,Cout_pad] dense, or NULL */
+  int32_t relu;
+} dreamb200_conv_desc;
+
+const char* dreamb200_last_error(void);
+int dreamb200_version(void);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+int64_t dreamb200_launch_count(void);
+
+int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream);
+
+/* x fp32 NCHW [B,3,H,W] -> out fp16 NHWC [B,Ho,Wo,Kpad]; k=(r*S+s)*3+c, zero padded */
+int dreamb200_im2col_first(const float* x, void* out, int B, int H, int W,
+                           int R, int S, int stride, int pad, int Ho, int Wo, int Kpad, void* stream);
+/* k x k / stride s / pad p max pool, NHWC fp16, floor mode */
+int dreamb200_maxpool_nhwc(const void* x, void* y, int B, int H, int W, int C,
+                           int k, int s, int p, int Ho, int Wo, void* stream);
+int dreamb200_upsample2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* fp16 NHWC [B,H,W,Cpad] -> fp32 NCHW [B,C,H,W] and back (debug / boundary) */
+int dreamb200_nhwc_f16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int Cpad, int C, void* stream);
+int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int H, int W, int C, int Cpad, void* stream);
+
+/* peaks_from_belief_maps for n_maps = B*K maps of h x w fp32 (contiguous).
+   gauss_w: 13 fp64 taps w[0..12] for |offset| 0..12 (host computes them like scipy).
+   scratch: 2*n_maps*h*w floats.  peak table: capacity `cap` per map, rows
+   (x:f64, y:f64, score:f32, pad) ; counts[n_maps] = true count (may exceed cap).
+   summary[n_maps*4] doubles: best x, best y, best score, second score. */
+int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
+                    double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
+                    int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
+
+int dreamb200_softargmax(const float* maps, const float* beta, float* out_xy,
+                         int B, int K, int H, int W, float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
