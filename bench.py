@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DREAM belief-map hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): DREAM-vgg-Q inference, batch 128 synthetic 400x400 RGB frames per
+GPU, 7 keypoints.  A "step" = one pass of the hot path over one batch: network forward (23 convs, pools,
+upsamples) + device peak extraction + keypoint selection, i.e. `DreamNetwork.inference`.
+  value : images/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : the same through the public API with HOST (pinned) inputs: H2D of the fp32 batch + inference
+          + D2H of the [B,7,2] keypoints inside the timed region.
+  roofline : tensor-pipe roofline of the dominant kernel (conv_tc_kernel<256>), algorithmic FLOPs /
+          CUDA-event duration measured live in an instrumented pass.
+  cpu_baseline : the oracle port of the reference's CPU PyTorch path timed on the host cores (N=1 only).
+Multi-GPU: frames shard across ranks with no collective ("weak" scaling: 128 frames per GPU per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMG = 141.7824          # vgg-Q @400x400 algorithmic conv FLOPs (SURVEY.md App. A / BASELINE.md)
+B_PER_GPU = 128
+H = W = 400
+K_KP = 7
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tensor_burst": d.get("bf16_tflops"), "tensor_sustained": d.get("bf16_tflops_sustained"),
+                "hbm": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor_burst": 1590.0, "tensor_sustained": 1400.0, "hbm": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_config():
+    names = ["panda_link0", "panda_link2", "panda_link3", "panda_link4", "panda_link6", "panda_link7", "panda_hand"]
+    return {
+        "architecture": {"type": "vgg", "target": "belief_maps", "input_heads": ["image_rgb"],
+                         "output_heads": ["belief_maps"],
+                         "image_normalization": {"mean": [0.5] * 3, "stdev": [0.5] * 3},
+                         "loss": {"type": "mse"}, "image_preprocessing": "shrink-and-crop"},
+        "manipulator": {"name": "panda", "keypoints": [{"name": n} for n in names]},
+        "training": {"config": {"net_input_resolution": [W, H]}, "platform": {"gpu_ids": []}},
+    }
+
+
+def cpu_baseline_sample(n_images, threads=None):
+    """The reference's CPU path (oracle port of dream/models.py + image_proc peaks) on `n_images` frames."""
+    import torch
+    from oracle import ref_models, ref_peaks
+    if threads:
+        torch.set_num_threads(threads)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(K_KP), seed=0, out_gain=13.0, mode="default")
+    x = torch.rand((n_images, 3, H, W), generator=torch.Generator().manual_seed(0)) * 2 - 1
+    with torch.no_grad():
+        ref_models.vgg_forward(sd, x[:1])                      # warm-up
+        t0 = time.perf_counter()
+        y = ref_models.vgg_forward(sd, x)
+        t_fwd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for b in range(n_images):
+            ref_peaks.select_keypoints(ref_peaks.peaks_from_belief_maps(y[b].numpy(), 0.4395))
+        t_peaks = time.perf_counter() - t0
+    return n_images / (t_fwd + t_peaks), t_fwd, t_peaks, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is
+    Python/PyTorch and cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 8
+    rates, times = [], []
+    for i in range(args.warmup_ref + args.steps_ref):
+        r, tf, tp, thr = cpu_baseline_sample(n)
+        if i >= args.warmup_ref:
+            rates.append(r)
+            times.append(tf + tp)
+    val = n * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DREAM-vgg-Q inference (forward + peak extraction), 400x400, 7 keypoints",
+                   "sample": "%d frames per step on the host CPU" % n},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": thr, "kind": "port",
+                         "sample": "%d steps x %d frames, oracle port of dream/models.py + image_proc peaks" %
+                                   (len(times), n)},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write per-layer timings (JSON) to this path")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    args.steps_ref = min(args.steps, 3)
+    args.warmup_ref = 1
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = _dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from dream_b200 import _lib, network, ops
+    from dream_b200 import image_proc
+
+    B = args.batch
+    net = network.create_network_from_config_data(make_config())
+    net.enable_evaluation()
+    model = net.model.module
+    # synthetic inputs of the named shape; two batches (157 MB > L2) rotate, and every step streams
+    # ~10 GB of activations, so nothing survives in the 126 MB L2 between timed iterations.
+    g = torch.Generator(device=dev).manual_seed(rank)
+    xs = [torch.rand((B, 3, H, W), device=dev, generator=g) * 2 - 1 for _ in range(2)]
+    host_x = [x.cpu().pin_memory() for x in xs]
+
+    def step_device(i):
+        with torch.no_grad():
+            belief = model.belief_maps(xs[i & 1])
+            table = image_proc.find_peaks_device(belief, 0.4395)
+            return image_proc.select_keypoints_device(table, 0.25)
+
+    def step_e2e(i):
+        with torch.no_grad():
+            x = host_x[i & 1].to(dev, non_blocking=True)
+            _, kps = net.inference(x)               # ends with the D2H copy of the keypoints
+            return kps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.finish() if sampler else None
+    value = world * B * args.steps / (ms / 1e3)
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- instrumented pass: per-launch CUDA-event durations of the tensor-core conv kernels ----
+    roof = None
+    if rank == 0:
+        peaks = _peaks()
+        ops.PROFILE = []
+        reps = 3
+        for i in range(reps):
+            step_device(i)
+        torch.cuda.synchronize()
+        recs = {}
+        for tag, flops, e0, e1 in ops.PROFILE:
+            r = recs.setdefault(tag, [0.0, 0.0, 0])
+            r[0] += e0.elapsed_time(e1); r[1] += flops; r[2] += 1
+        ops.PROFILE = None
+        total_ms = sum(r[0] for r in recs.values()) / reps
+        fam = {}
+        for tag, (t, f, n) in recs.items():
+            k = tag.split(" ")[0]
+            a = fam.setdefault(k, [0.0, 0.0, 0])
+            a[0] += t; a[1] += f; a[2] += n
+        dom = max(fam, key=lambda k: fam[k][0])
+        dt, df, dn = fam[dom]
+        achieved = df / dt / 1e9                       # TFLOP/s (flops / ms / 1e9)
+        peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_kind": "bf16 dense sustained, " + peaks["source"],
+                "launches_per_step": dn // reps, "kernel_ms_per_step": dt / reps,
+                "kernel_share_of_conv_time": dt / reps / total_ms,
+                "conv_stack": {"ms_per_step": total_ms,
+                               "algorithmic_tflops": GFLOP_PER_IMG * B / total_ms,
+                               "frac_of_peak": GFLOP_PER_IMG * B / total_ms / peak},
+                "whole_step": {"algorithmic_tflops": value / world * GFLOP_PER_IMG / 1e3,
+                               "frac_of_peak": value / world * GFLOP_PER_IMG / 1e3 / peak}}
+        table = [{"layer": tag, "ms": t / reps, "tflops": f / t / 1e9, "launches": n // reps}
+                 for tag, (t, f, n) in sorted(recs.items(), key=lambda kv: -kv[1][0])]
+        if args.layer_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.layer_table)), exist_ok=True)
+            json.dump({"batch": B, "layers": table, "roofline": roof}, open(args.layer_table, "w"), indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, tf, tp, thr = cpu_baseline_sample(8)
+        cpu = {"value": r, "unit": "images/s", "cores": thr, "kind": "port",
+               "sample": "8 frames 400x400: oracle port of dream/models.py forward (%.2f s) + image_proc peaks (%.2f s)"
+                         % (tf, tp)}
+
+    if rank == 0:
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": "DREAM-vgg-Q inference (forward + peak extraction), batch %d/GPU, 400x400, "
+                                   "7 keypoints" % B,
+                       "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                       "l2": "inputs rotate over 2 batches (157 MB > 126 MB L2); ~10 GB of activations stream per step"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+                    "d2h_bytes_per_step": B * K_KP * 2 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ class ConvDesc(C.Structure):
         ("out_mode", C.c_int32), ("cout_real", C.c_int32),
         ("residual", C.c_void_p),
         ("relu", C.c_int32),
+        ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p),
     ]
 
 
@@ -41,11 +42,19 @@ _PROTOS = {
     "dreamb200_im2col_first": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
     "dreamb200_maxpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "dreamb200_upsample2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dreamb200_add_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dreamb200_nhwc_f16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "dreamb200_nchw_f32_to_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "dreamb200_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "dreamb200_nhwc_to_cm_f16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 +
+                        [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dreamb200_relu_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dreamb200_upsample2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dreamb200_bias_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_softargmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 +
                              [C.c_void_p, C.c_void_p]),
 }

@@ -1,0 +1,120 @@
+"""Training forward/backward of DreamHourglass (vgg-Q family) on the hand-written kernels.
+
+Reference: `DreamNetwork.train` -> `loss.backward()` (dream/network.py:328-338) differentiates
+DreamHourglass.forward (dream/models.py:761-827) with torch autograd over cuDNN ops.  Here the whole
+network is ONE `torch.autograd.Function`: forward runs the same kernel plan as inference while keeping
+every layer's fp16 NHWC activation, backward walks the tape in reverse:
+
+    dY --(ReLU mask from the saved output)--> bias grad (column sums)
+       --> weight grad : dreamb200_wgrad   (tcgen05 GEMM over the pixel axis, split-K, fp32 atomics)
+       --> data grad   : dreamb200_conv2d_fwd with the 180-degree-rotated, Cin<->Cout swapped weights
+    2x2 max-pool / nearest-upsample backward in between.
+
+The MSE / Huber loss and the optimizer stay PyTorch (north_star): the loss gradient arrives as
+`grad_output` (fp32 NCHW) and parameter gradients leave as fp32 tensors in PyTorch OIHW layout.
+fp16 has a narrow exponent range, so `grad_output` is multiplied by a power-of-two loss scale computed
+on the device (no host sync) and parameter gradients are un-scaled in fp32.
+"""
+import torch
+
+from . import models, ops
+
+
+def _dgrad_pack(weight, cin_pad, cout_pad):
+    """Weights for the data gradient of a 3x3 'same' conv: dX[q] = sum_rs dY[q-(r-1,s-1)] W[:,:,r,s]^T."""
+    wt = weight.detach().permute(1, 0, 2, 3)          # [Cin, Cout, 3, 3]: "output" channels are Cin now
+    rs = [(r, s) for r in range(3) for s in range(3)]
+    w = ops.pack_conv_weight(wt, rs, cin_pad=cout_pad, cout_pad=cin_pad)
+    taps = [(1 - r, 1 - s) for r, s in rs]
+    return w, taps
+
+
+class _HourglassTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        P = model.plan()
+        tape = []          # (kind, key, input, output)
+        t = ops.im2col_first(x, 3, 3, 1, 1, 64)
+        y = models._run_conv(P["first"], t)
+        tape.append(("first", "layer_0_1_down.0", t, y))
+        t = y
+        for bi, (block, idxs, _) in enumerate(models.VGG_TRUNK):
+            if bi > 0:
+                y = ops.maxpool(t, 2, 2, 0)
+                tape.append(("pool", None, t, y))
+                t = y
+            for j in idxs:
+                if block == "layer_0_1_down" and j == 0:
+                    continue
+                key = "%s.%d" % (block, j)
+                y = models._run_conv(P[key], t)
+                tape.append(("conv", key, t, y))
+                t = y
+        stages = [("upsample_0_4", ".4", ".6"), ("upsample_0_3", ".4", ".6")]
+        if model.full_output:
+            stages += [("upsample_0_2", ".2", ".4"), ("upsample_0_1", ".2", ".4")]
+        for name, a, b in stages:
+            y = ops.upsample2(t)
+            tape.append(("up", None, t, y))
+            t = y
+            for suffix in (a, b):
+                y = models._run_conv(P[name + suffix], t)
+                tape.append(("conv", name + suffix, t, y))
+                t = y
+        for key in ("heads_0.0", "heads_0.2"):
+            y = models._run_conv(P[key], t)
+            tape.append(("conv", key, t, y))
+            t = y
+        out = models._run_conv(P["heads_0.4"], t, head_cout=model.n_keypoints)
+        tape.append(("head", "heads_0.4", t, None))
+        ctx.tape = tape
+        ctx.model = model
+        ctx.param_names = [n for n, _ in model.named_parameters()]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, tape = ctx.model, ctx.tape
+        P = model.plan()
+        grads = {}
+        go = grad_out.contiguous().float()
+        # power-of-two loss scale so the largest |dY| sits near 2^8 in fp16 (computed on device)
+        amax = go.abs().amax().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(256.0 / amax)))
+        inv = 1.0 / scale
+        g = ops.nchw_to_nhwc_f16((go * scale).contiguous(), 64)           # [B,h,w,64], channels >= K are zero
+        for kind, key, xin, yout in reversed(tape):
+            if kind in ("conv", "head", "first"):
+                node = models._node_for(model, key)
+                pc = P["first"] if kind == "first" else P[key]
+                if pc.relu:
+                    ops.relu_mask_(g, yout)
+                cout, cin = node.weight.shape[0], node.weight.shape[1]
+                if node.bias is not None:
+                    grads[key + ".bias"] = ops.bias_grad(g)[:cout] * inv
+                if kind == "first":
+                    dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]                   # [co, (r,s,c)]
+                    grads[key + ".weight"] = (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                    g = None                                                           # the image needs no grad
+                else:
+                    dw = ops.wgrad(g, xin, ops.TAPS_3x3)[:, :cout, :cin]               # [9, co, ci]
+                    grads[key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
+                    wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
+                    B, H, W, _ = xin.shape
+                    g = ops.conv_taps(g, wd, None, taps, H, W)
+            elif kind == "pool":
+                g = ops.maxpool2_bwd(xin, g)
+            elif kind == "up":
+                g = ops.upsample2_bwd(g)
+        ctx.tape = None
+        return (None, None) + tuple(grads.get(n) for n in ctx.param_names)
+
+
+def hourglass_train_forward(model, x):
+    if model.deconv_decoder or model.skip_connections:
+        raise NotImplementedError(
+            "dream_b200 training currently covers the upsample-decoder DreamHourglass (vgg-Q family); "
+            "deconv_decoder / skip_connections training is not built yet (inference is).")
+    x = model._check_input(x)
+    params = [p for _, p in model.named_parameters()]
+    return _HourglassTrainFn.apply(model, x, *params)

@@ -135,6 +135,20 @@ __global__ void upsample2_nhwc_kernel(const uint4* __restrict__ x, uint4* __rest
   }
 }
 
+// y += x, fp16, 8 elements per thread (hourglass skip connections, models.py:775-799)
+__global__ void add_f16_kernel(uint4* __restrict__ y, const uint4* __restrict__ x, long long n8) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    uint4 a = y[idx];
+    const uint4 b = __ldg(x + idx);
+    __half2* ah = reinterpret_cast<__half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ah[j] = __hadd2(ah[j], bh[j]);
+    y[idx] = a;
+  }
+}
+
 // fp16 NHWC [B,H,W,Cpad] -> fp32 NCHW [B,C,H,W]; a 32-pixel x 32-channel smem transpose per block step
 __global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, int B,
                                             long long HW, int Cpad, int C) {
@@ -258,6 +272,16 @@ extern "C" int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, in
   const long long tiles = (long long)B * ((HW + 31) / 32) * ((Cpad + 31) / 32);
   nchw_f32_to_nhwc_f16_kernel<<<grid_for(tiles * 256, 256), 256, 0, (cudaStream_t)stream>>>(
       x, reinterpret_cast<__half*>(y), B, HW, C, Cpad);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_add_f16(void* y, const void* x, long long n, void* stream) {
+  DB_REQUIRE(y && x, "add_f16: null pointer");
+  DB_REQUIRE(n > 0 && n % 8 == 0, "add_f16: n=%lld must be a positive multiple of 8", n);
+  add_f16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint4*>(y), reinterpret_cast<const uint4*>(x), n / 8);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -31,6 +31,8 @@ struct ConvParams {
   int8_t dy[DREAMB200_MAX_TAPS], dx[DREAMB200_MAX_TAPS];
   const float* bias;
   const __half* residual;
+  const float* residual_f32;   // fp32 NHWC residual stream (ResNet identity path), or NULL
+  float* y_f32;                // optional fp32 NHWC copy of the output (next block's identity)
   int Cout_pad;
   int relu;
   float* out_f32;
@@ -182,8 +184,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
         const __half* res_row = nullptr;
-        if (p.residual != nullptr && valid)
-          res_row = p.residual + ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
+        const float* res32_row = nullptr;
+        float* y32_row = nullptr;
+        const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
+        if (p.residual != nullptr && valid) res_row = p.residual + row_off;
+        if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
+        if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
           const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
@@ -218,9 +224,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
+            if (res32_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
+                f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
+              }
+            }
             if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            }
+            if (y32_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) =
+                    make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -304,9 +323,9 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                    const uint32_t* estride, const char* what) {
+int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                        const uint32_t* estride, const char* what) {
   PFN_encodeTiled enc = get_encode();
   DB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
@@ -339,6 +358,8 @@ static void choose_tile(int Wo, int Ho, int in_stride, int* tw_out, int* th_out)
   *th_out = bth;
 }
 
+int device_sm_count();
+
 template <int BLOCK_N, int OUT_MODE>
 static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
   ConvParams p;
@@ -358,6 +379,8 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   memcpy(p.dx, d->tap_dx, sizeof(p.dx));
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.residual_f32 = d->residual_f32;
+  p.y_f32 = d->y_f32;
   p.Cout_pad = d->Cout_pad;
   p.relu = d->relu;
   p.out_f32 = (OUT_MODE == DREAMB200_OUT_NCHW_F32) ? reinterpret_cast<float*>(d->y) : nullptr;
@@ -382,21 +405,21 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
     uint32_t box[4] = {64, (uint32_t)p.tw * s, (uint32_t)p.th * s, 1};
     uint32_t es[4] = {1, s, s, 1};
     DB_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv: TMA box too large (%u x %u)", box[1], box[2]);
-    if (make_map(&tmA, d->x, 4, dims, str, box, es, "activation")) return -1;
+    if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es, "activation")) return -1;
   }
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->taps};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
     uint32_t box[3] = {64, (uint32_t)BLOCK_N, 1};
     uint32_t es[3] = {1, 1, 1};
-    if (make_map(&tmB, d->w, 3, dims, str, box, es, "weights")) return -1;
+    if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "weights")) return -1;
   }
   if (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
     uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
     uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
     uint32_t es[4] = {1, 1, 1, 1};
-    if (make_map(&tmC, d->y, 4, dims, str, box, es, "output")) return -1;
+    if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "output")) return -1;
   }
 
   auto kern = conv_tc_kernel<BLOCK_N, OUT_MODE>;
@@ -412,7 +435,7 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   return 0;
 }
 
-static int sm_count() {
+int device_sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -437,11 +460,12 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
   DB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "conv: empty tensor");
   DB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0,
              "conv: tensors must be 16-byte aligned");
-  const int sms = sm_count();
+  const int sms = device_sm_count();
   if (d->out_mode == DREAMB200_OUT_NCHW_F32) {
     DB_REQUIRE(d->Cout_pad == 16, "conv: NCHW_F32 head needs Cout_pad == 16 (got %d)", d->Cout_pad);
     DB_REQUIRE(d->cout_real >= 1 && d->cout_real <= 16, "conv: cout_real=%d out of range", d->cout_real);
-    DB_REQUIRE(d->residual == nullptr, "conv: residual unsupported for the NCHW_F32 head");
+    DB_REQUIRE(d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr,
+               "conv: residual / fp32 stream unsupported for the NCHW_F32 head");
     return launch<16, DREAMB200_OUT_NCHW_F32>(d, stream, sms);
   }
   DB_REQUIRE(d->out_mode == DREAMB200_OUT_NHWC_F16, "conv: unknown out_mode %d", d->out_mode);

@@ -1,0 +1,306 @@
+// peaks.cu -- device-side keypoint extraction from belief maps.
+//
+// dreamb200_peaks reproduces dream/image_proc.py:914-1018 (peaks_from_belief_maps) for all B*K maps
+// of a batch in three launches, bit-for-bit on the integer peak set:
+//   1. gauss_pass<0>: scipy.ndimage.gaussian_filter axis-0 pass (image_proc.py:935).  fp64 accumulation
+//      in scipy's exact order -- centre tap first, then symmetric pairs from the farthest inwards,
+//      (lo+hi)*w added with separate rounding (no FMA: scipy's C is built without contraction) --
+//      "reflect" boundary, result rounded to fp32 exactly once, like scipy's fp32 output array.
+//   2. gauss_pass<1>: the axis-1 pass on the fp32 intermediate.
+//   3. collect_peaks: one CTA per map.  4-neighbour >= test against zero-padded shifts and > 0.01f
+//      (image_proc.py:936-954), ordered (raster) compaction, 5x5 weighted centroid on the UNsmoothed
+//      map in fp64 with numpy's pairwise summation order (image_proc.py:961-998), plus the
+//      best / second-best scores needed by DreamNetwork.inference (network.py:548-577).
+// All three are HBM/L2 streaming kernels over 4*B*K*h*w bytes.
+//
+// dreamb200_softargmax: SoftArgmaxPavlo.forward (dream/spatial_softmax.py:24-95), one CTA per map.
+#include "common.cuh"
+#include "dreamb200.h"
+
+namespace db200 {
+
+constexpr int kMaxRadius = 32;
+struct GaussW {
+  double w[kMaxRadius + 1];
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i >= n ? period - 1 - i : i;
+}
+
+template <int AXIS>
+__global__ void gauss_pass_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_maps, int h,
+                                  int w, const __grid_constant__ GaussW gw, int radius) {
+  const long long total = n_maps * h * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % w);
+    const long long r = idx / w;
+    const int y = (int)(r % h);
+    const float* m = in + (r / h) * (long long)h * w;
+    const int n = AXIS == 0 ? h : w;
+    const int c = AXIS == 0 ? y : x;
+    double acc = __dmul_rn((double)m[(size_t)y * w + x], gw.w[0]);
+    for (int d = radius; d >= 1; --d) {
+      int lo = c - d, hi = c + d;
+      if (lo < 0 || hi >= n) {
+        lo = reflect_idx(lo, n);
+        hi = reflect_idx(hi, n);
+      }
+      const double a = AXIS == 0 ? (double)m[(size_t)lo * w + x] : (double)m[(size_t)y * w + lo];
+      const double b = AXIS == 0 ? (double)m[(size_t)hi * w + x] : (double)m[(size_t)y * w + hi];
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), gw.w[d]));
+    }
+    out[idx] = __double2float_rn(acc);
+  }
+}
+
+// numpy pairwise sum of a contiguous 25-vector: 8 partials over the first 24, tree combine, tail.
+__device__ __forceinline__ double pairwise25(const double* v) {
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+#pragma unroll
+  for (int i = 8; i < 24; i += 8)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], v[i + j]);
+  const double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  return __dadd_rn(res, v[24]);
+}
+
+struct Top2 {
+  float s0, s1;      // best and second-best score (NaN-free inputs assumed)
+  int i0;            // raster index of the best (ties -> earliest), -1 if none
+  int n;             // how many candidates merged (0, 1, 2+)
+  double x0, y0;
+};
+
+__device__ __forceinline__ void top2_insert(Top2& t, float s, int idx, double x, double y) {
+  if (t.n == 0) {
+    t.s0 = s; t.i0 = idx; t.x0 = x; t.y0 = y; t.n = 1;
+  } else if (s > t.s0 || (s == t.s0 && idx < t.i0)) {
+    t.s1 = t.s0; t.s0 = s; t.i0 = idx; t.x0 = x; t.y0 = y; t.n = 2;
+  } else if (t.n == 1 || s > t.s1) {
+    t.s1 = s; t.n = 2;
+  }
+}
+
+constexpr int kPeakThreads = 256;
+
+__global__ void __launch_bounds__(kPeakThreads)
+collect_peaks_kernel(const float* __restrict__ ori, const float* __restrict__ smooth, int h, int w,
+                     double offset, int cap, double* __restrict__ peak_xy, float* __restrict__ peak_score,
+                     int32_t* __restrict__ peak_ij, int32_t* __restrict__ counts, double* __restrict__ summary) {
+  const long long map = blockIdx.x;
+  const float* mo = ori + map * (long long)h * w;
+  const float* ms = smooth + map * (long long)h * w;
+  __shared__ int warp_cnt[kPeakThreads / 32];
+  __shared__ int base_s;
+  __shared__ Top2 tops[kPeakThreads];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) base_s = 0;
+  Top2 mine;
+  mine.n = 0; mine.i0 = -1; mine.s0 = 0.f; mine.s1 = 0.f; mine.x0 = 0.0; mine.y0 = 0.0;
+  __syncthreads();
+  const int total = h * w;
+  for (int start = 0; start < total; start += kPeakThreads) {
+    const int idx = start + tid;
+    bool is_peak = false;
+    int px = 0, py = 0;
+    if (idx < total) {
+      py = idx / w;
+      px = idx - py * w;
+      const float v = ms[idx];
+      const float up = py > 0 ? ms[idx - w] : 0.0f;
+      const float dn = py < h - 1 ? ms[idx + w] : 0.0f;
+      const float lf = px > 0 ? ms[idx - 1] : 0.0f;
+      const float rt = px < w - 1 ? ms[idx + 1] : 0.0f;
+      is_peak = (v >= up) && (v >= dn) && (v >= lf) && (v >= rt) && (v > 0.01f);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_peak);
+    if (lane == 0) warp_cnt[wid] = __popc(ballot);
+    __syncthreads();
+    int before = base_s;
+    int chunk_total = 0;
+#pragma unroll
+    for (int i = 0; i < kPeakThreads / 32; ++i) {
+      const int c = warp_cnt[i];
+      if (i < wid) before += c;
+      chunk_total += c;
+    }
+    if (is_peak) {
+      const int slot = before + __popc(ballot & ((1u << lane) - 1u));
+      double wts[25], xv[25], yv[25];
+#pragma unroll
+      for (int k = 0; k < 25; ++k) { wts[k] = 0.0; xv[k] = 0.0; yv[k] = 0.0; }
+#pragma unroll
+      for (int i = -2; i <= 2; ++i) {       // row offset
+#pragma unroll
+        for (int j = -2; j <= 2; ++j) {     // column offset
+          const int yy = py + i, xx = px + j;
+          if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+          const int k = (j + 2) * 5 + (i + 2);
+          wts[k] = (double)mo[(size_t)yy * w + xx];
+          xv[k] = (double)xx;
+          yv[k] = (double)yy;
+        }
+      }
+      const double scl = pairwise25(wts);
+      double cx, cy;
+      if (scl == 0.0) {
+        cx = (double)px + offset;
+        cy = (double)py + offset;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 25; ++k) { xv[k] = __dmul_rn(xv[k], wts[k]); yv[k] = __dmul_rn(yv[k], wts[k]); }
+        cx = __dadd_rn(__ddiv_rn(pairwise25(xv), scl), offset);
+        cy = __dadd_rn(__ddiv_rn(pairwise25(yv), scl), offset);
+      }
+      const float score = mo[idx];
+      if (slot < cap) {
+        const size_t o = (size_t)map * cap + slot;
+        peak_xy[2 * o] = cx;
+        peak_xy[2 * o + 1] = cy;
+        peak_score[o] = score;
+        peak_ij[2 * o] = px;
+        peak_ij[2 * o + 1] = py;
+      }
+      top2_insert(mine, score, idx, cx, cy);
+    }
+    __syncthreads();
+    if (tid == 0) base_s += chunk_total;
+    __syncthreads();
+  }
+  tops[tid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    Top2 t = tops[0];
+    for (int i = 1; i < kPeakThreads; ++i) {
+      const Top2& o = tops[i];
+      if (o.n == 0) continue;
+      const float o_s1 = o.s1;
+      const int o_n = o.n;
+      top2_insert(t, o.s0, o.i0, o.x0, o.y0);
+      if (o_n >= 2) {
+        // second of the other set can only become our second (index irrelevant for the runner-up)
+        if (t.n == 1 || o_s1 > t.s1) { t.s1 = o_s1; t.n = 2; }
+      }
+    }
+    counts[map] = base_s;
+    summary[4 * map + 0] = t.x0;
+    summary[4 * map + 1] = t.y0;
+    summary[4 * map + 2] = (double)t.s0;
+    summary[4 * map + 3] = (double)t.s1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SoftArgmaxPavlo: 7x7 average pool (zero padded, /49) -> max -> exp(beta*(v-max)) -> expected x,y
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+softargmax_kernel(const float* __restrict__ maps, const float* __restrict__ beta, float* __restrict__ out_xy,
+                  int K, int H, int W, float* __restrict__ scratch) {
+  const long long map = blockIdx.x;
+  const float* m = maps + map * (long long)H * W;
+  float* pooled = scratch + map * (long long)H * W;
+  __shared__ float shf[8];
+  __shared__ double shd[8];
+  const float b = beta[map % K];
+  float vmax = -INFINITY;
+  for (int idx = threadIdx.x; idx < H * W; idx += blockDim.x) {
+    const int y = idx / W, x = idx - y * W;
+    float s = 0.0f;
+    for (int dy = -3; dy <= 3; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -3; dx <= 3; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        s += m[(size_t)yy * W + xx];
+      }
+    }
+    s = s / 49.0f;
+    pooled[idx] = s;
+    vmax = fmaxf(vmax, s);
+  }
+  vmax = block_reduce_max(vmax, shf);
+  double se = 0.0, sx = 0.0, sy = 0.0;
+  for (int idx = threadIdx.x; idx < H * W; idx += blockDim.x) {
+    const int y = idx / W, x = idx - y * W;
+    const float e = expf(b * (pooled[idx] - vmax));
+    se += (double)e;
+    sx += (double)e * x;
+    sy += (double)e * y;
+  }
+  se = block_reduce_sum(se, shd);
+  sx = block_reduce_sum(sx, shd);
+  sy = block_reduce_sum(sy, shd);
+  if (threadIdx.x == 0) {
+    const double den = se + 1e-8;
+    out_xy[2 * map] = (float)(sx / den);
+    out_xy[2 * map + 1] = (float)(sy / den);
+  }
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
+                               double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
+                               int32_t* peak_ij, int32_t* counts, double* summary, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  DB_REQUIRE(maps && gauss_w && scratch && peak_xy && peak_score && peak_ij && counts && summary,
+             "peaks: null pointer");
+  DB_REQUIRE(n_maps > 0 && h > 0 && w > 0, "peaks: empty input (n_maps=%d h=%d w=%d)", n_maps, h, w);
+  DB_REQUIRE(radius >= 0 && radius <= kMaxRadius, "peaks: radius %d out of range", radius);
+  DB_REQUIRE(cap >= 1, "peaks: cap must be >= 1");
+  DB_REQUIRE((long long)h * w < (1ll << 30), "peaks: map too large");
+  GaussW gw;
+  for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
+  const long long total = (long long)n_maps * h * w;
+  float* tmp = scratch;
+  float* smooth = scratch + total;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gauss_pass_kernel<0><<<(int)blocks, 256, 0, stream>>>(maps, tmp, n_maps, h, w, gw, radius);
+  gauss_pass_kernel<1><<<(int)blocks, 256, 0, stream>>>(tmp, smooth, n_maps, h, w, gw, radius);
+  collect_peaks_kernel<<<n_maps, kPeakThreads, 0, stream>>>(maps, smooth, h, w, offset, cap, peak_xy, peak_score,
+                                                          peak_ij, counts, summary);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch(3);
+  return 0;
+}
+
+extern "C" int dreamb200_softargmax(const float* maps, const float* beta, float* out_xy, int B, int K, int H,
+                                    int W, float* scratch, void* stream_v) {
+  DB_REQUIRE(maps && beta && out_xy && scratch, "softargmax: null pointer");
+  DB_REQUIRE(B > 0 && K > 0 && H > 0 && W > 0, "softargmax: empty input");
+  softargmax_kernel<<<B * K, 256, 0, (cudaStream_t)stream_v>>>(maps, beta, out_xy, K, H, W, scratch);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}

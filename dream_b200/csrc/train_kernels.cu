@@ -1,0 +1,447 @@
+// train_kernels.cu -- backward pass of the DREAM networks (reference: `loss.backward()` in
+// dream/network.py:328-338, i.e. autograd of nn.Conv2d / MaxPool2d / Upsample / ReLU in
+// dream/models.py:591-747).
+//
+//   data gradient  : dX = conv(dY, W rotated 180 deg, Cin<->Cout swapped) -> the forward tensor-core kernel
+//                    (conv_tc.cu) with re-packed weights; nothing new here.
+//   weight gradient: dW[tap][co][ci] = sum_p dY[p][co] * X[p + tap][ci]   (this file, wgrad_tc_kernel):
+//                    a GEMM whose reduction axis is the pixel index.  Both operands are staged as
+//                    K-major tiles by TMA from channel-major (NCHW, row pitch padded to 8) fp16 copies:
+//                    a box of (bx x by) = 64 pixels x 128|N channels lands as rows of 128 B per channel,
+//                    the same canonical SWIZZLE_128B layout the forward kernel feeds to tcgen05.mma.  The
+//                    tap shift and the zero padding are TMA coordinates / out-of-bounds fill.  Split-K over
+//                    pixel ranges across CTAs, fp32 accumulation in TMEM, fp32 atomics into dW.
+//   plus the HBM-bound pieces: ReLU mask, 2x2 max-pool backward, nearest-upsample backward, bias
+//   gradient (column sums) and the NHWC -> channel-major transposes.
+#include "common.cuh"
+#include "dreamb200.h"
+
+namespace db200 {
+
+int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride,
+                        const char* what);
+int device_sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// wgrad on tcgen05
+// ---------------------------------------------------------------------------------------------
+struct WgradParams {
+  int B, H, W;              // activation extent (dY and X have the same H x W: stride-1 'same' convs)
+  int bx, by;               // pixel patch per k-block (bx*by == 64)
+  int px_tiles, py_tiles;   // patches per image
+  int taps;
+  int8_t dy[DREAMB200_MAX_TAPS], dx[DREAMB200_MAX_TAPS];
+  int co_tiles, ci_tiles;   // 128-row output tiles, BLOCK_N-column tiles
+  int splits;               // split-K factor
+  long long kblocks_total;  // B * py_tiles * px_tiles
+  float* dw;                // fp32 [taps][Cout_pad][Cin_pad], accumulated with atomics
+  int Cout_pad, Cin_pad;
+  int stages;
+};
+
+constexpr int kWgThreads = 192;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ WgradParams p) {
+  constexpr int kABytes = 128 * 128;
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * stages);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // work unit of this CTA: (split, tap, co tile, ci tile); CTAs with the same split are adjacent
+  int u = blockIdx.x;
+  const int ci_t = u % p.ci_tiles; u /= p.ci_tiles;
+  const int co_t = u % p.co_tiles; u /= p.co_tiles;
+  const int tap = u % p.taps;
+  const int split = u / p.taps;
+  const long long kb_lo = p.kblocks_total * split / p.splits;
+  const long long kb_hi = p.kblocks_total * (split + 1) / p.splits;
+  const int n_kb = (int)(kb_hi - kb_lo);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int patches = p.px_tiles * p.py_tiles;
+      for (long long kb = kb_lo; kb < kb_hi; ++kb) {
+        const int b = (int)(kb / patches);
+        const int r = (int)(kb - (long long)b * patches);
+        const int ty = r / p.px_tiles, tx = r - ty * p.px_tiles;
+        const int x0 = tx * p.bx, y0 = ty * p.by;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
+        tma_load_4d(sa, &tmDY, full_bar(stage), x0, y0, co_t * 128, b);
+        tma_load_4d(sa + kABytes, &tmX, full_bar(stage), x0 + p.dx[tap], y0 + p.dy[tap], ci_t * BLOCK_N, b);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint64_t adesc = umma_desc_k_sw128(sa);
+        const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else if (n_kb > 0) {
+    // epilogue: 128 accumulator rows (co) x BLOCK_N columns (ci) -> fp32 atomics
+    const int q = warp & 3;
+    const int co = co_t * 128 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* out = p.dw + ((size_t)tap * p.Cout_pad + co) * p.Cin_pad + ci_t * BLOCK_N;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_wait_ld();
+      if (co < p.Cout_pad) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(out + c * 32 + i, __uint_as_float(v[i]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradParams& p, cudaStream_t stream) {
+  constexpr int kStageBytes = 128 * 128 + BLOCK_N * 128;
+  int stages = (232448 - 1024 - 512) / kStageBytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * kStageBytes + 512;
+  auto kern = wgrad_tc_kernel<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int grid = p.splits * p.taps * p.co_tiles * p.ci_tiles;
+  kern<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming kernels
+// ---------------------------------------------------------------------------------------------
+// NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp = W rounded up to 8, pad columns zero)
+__global__ void nhwc_to_cm_f16_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W,
+                                      int C, int Wp) {
+  __shared__ __half tile[32][34];
+  const int xtiles = (Wp + 31) / 32, ctiles = C / 32;
+  const long long total = (long long)B * H * xtiles * ctiles;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % ctiles);
+    long long r = t / ctiles;
+    const int xt = (int)(r % xtiles);
+    r /= xtiles;
+    const int yy = (int)(r % H);
+    const int b = (int)(r / H);
+    for (int i = ty; i < 32; i += 8) {
+      const int xx = xt * 32 + i;
+      __half v = __float2half(0.0f);
+      if (xx < W) v = x[((size_t)((size_t)b * H + yy) * W + xx) * C + ct * 32 + tx];
+      tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int xx = xt * 32 + tx;
+      if (xx < Wp) y[((size_t)((size_t)b * C + ct * 32 + i) * H + yy) * Wp + xx] = tile[tx][i];
+    }
+    __syncthreads();
+  }
+}
+
+// dy *= (y > 0), fp16, 8 per thread
+__global__ void relu_mask_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, long long n8) {
+  const __half2 zero = __float2half2_rn(0.0f);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    uint4 g = dy[idx];
+    const uint4 a = __ldg(y + idx);
+    __half2* gh = reinterpret_cast<__half2*>(&g);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gh[j] = __hmul2(gh[j], __hgt2(ah[j], zero));
+    dy[idx] = g;
+  }
+}
+
+// 2x2/s2 max-pool backward (floor mode): gradient goes to the first maximum of each window (ATen order)
+__global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                    int B, int H, int W, int C8, int Ho, int Wo) {
+  const long long total = (long long)B * H * W * C8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    long long pix = idx / C8;
+    const int ix = (int)(pix % W);
+    pix /= W;
+    const int iy = (int)(pix % H);
+    const int b = (int)(pix / H);
+    const int oy = iy >> 1, ox = ix >> 1;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (oy < Ho && ox < Wo) {
+      const size_t base = ((size_t)((size_t)b * H + 2 * oy) * W + 2 * ox) * C8 + c;
+      uint4 v[4];
+      v[0] = __ldg(x + base);
+      v[1] = __ldg(x + base + C8);
+      v[2] = __ldg(x + base + (size_t)W * C8);
+      v[3] = __ldg(x + base + (size_t)W * C8 + C8);
+      const uint4 g = __ldg(dy + ((size_t)((size_t)b * Ho + oy) * Wo + ox) * C8 + c);
+      const int me = (iy & 1) * 2 + (ix & 1);
+      const __half* gh = reinterpret_cast<const __half*>(&g);
+      __half* oh = reinterpret_cast<__half*>(&out);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int arg = 0;
+        float best = __half2float(reinterpret_cast<const __half*>(&v[0])[j]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float f = __half2float(reinterpret_cast<const __half*>(&v[k])[j]);
+          if (f > best) { best = f; arg = k; }
+        }
+        oh[j] = arg == me ? gh[j] : __float2half(0.0f);
+      }
+    }
+    dx[idx] = out;
+  }
+}
+
+// nearest x2 upsample backward: dx = sum of the 2x2 block of dy (fp32 sum, fp16 store)
+__global__ void upsample2_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int B, int H, int W,
+                                     int C8) {
+  const long long total = (long long)B * H * W * C8;
+  const int Wo = 2 * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    long long pix = idx / C8;
+    const int ix = (int)(pix % W);
+    pix /= W;
+    const int iy = (int)(pix % H);
+    const int b = (int)(pix / H);
+    const size_t base = ((size_t)((size_t)b * 2 * H + 2 * iy) * Wo + 2 * ix) * C8 + c;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 v = __ldg(dy + base + (size_t)(k >> 1) * Wo * C8 + (size_t)(k & 1) * C8);
+      const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(vh[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    uint4 o;
+    __half2 h;
+    h = __floats2half2_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    dx[idx] = o;
+  }
+}
+
+// bias gradient: db[c] += sum over rows of dy[row][c]  (dy fp16 [rows, C], db fp32 zeroed by the caller)
+__global__ void bias_grad_kernel(const __half* __restrict__ dy, float* __restrict__ db, long long rows, int C) {
+  // block = 256 threads: 32 channel-pairs (64 channels) x 8 row lanes; grid.y = channel groups of 64
+  const int cg = blockIdx.y;
+  const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+  const int c = cg * 64 + tc * 2;
+  float a0 = 0.0f, a1 = 0.0f;
+  for (long long r = (long long)blockIdx.x * 8 + tr; r < rows; r += (long long)gridDim.x * 8) {
+    const __half2 v = *reinterpret_cast<const __half2*>(dy + (size_t)r * C + c);
+    const float2 f = __half22float2(v);
+    a0 += f.x;
+    a1 += f.y;
+  }
+  __shared__ float sh[8][64];
+  sh[tr][tc * 2] = a0;
+  sh[tr][tc * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+    atomicAdd(db + cg * 64 + threadIdx.x, s);
+  }
+}
+
+static int grid_cap(long long work, int threads) {
+  long long blocks = (work + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, int B, int H, int W, int Wp,
+                               int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                               void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  DB_REQUIRE(dy_cm && x_cm && dw && tap_dy && tap_dx, "wgrad: null pointer");
+  DB_REQUIRE(Wp % 8 == 0 && Wp >= W, "wgrad: row pitch Wp=%d must be a multiple of 8 and >= W", Wp);
+  DB_REQUIRE(Cout_pad % 64 == 0, "wgrad: Cout_pad=%d must be a multiple of 64", Cout_pad);
+  DB_REQUIRE(Cin_pad % 64 == 0, "wgrad: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  DB_REQUIRE(taps >= 1 && taps <= DREAMB200_MAX_TAPS, "wgrad: taps=%d out of range", taps);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W;
+  // patch shape: bx in {8,16,32,64}, the one that wastes the fewest padded pixels
+  long best = -1;
+  for (int bx = 8; bx <= 64; bx *= 2) {
+    const int by = 64 / bx;
+    const long tiles = (long)((W + bx - 1) / bx) * ((H + by - 1) / by);
+    if (best < 0 || tiles < best) { best = tiles; p.bx = bx; p.by = by; }
+  }
+  p.px_tiles = (W + p.bx - 1) / p.bx;
+  p.py_tiles = (H + p.by - 1) / p.by;
+  p.taps = taps;
+  memcpy(p.dy, tap_dy, taps);
+  memcpy(p.dx, tap_dx, taps);
+  const int block_n = Cin_pad % 256 == 0 ? 256 : Cin_pad % 128 == 0 ? 128 : 64;
+  p.co_tiles = (Cout_pad + 127) / 128;   // a half-empty last tile is zero-filled by TMA
+  p.ci_tiles = Cin_pad / block_n;
+  p.kblocks_total = (long long)B * p.px_tiles * p.py_tiles;
+  const int units = taps * p.co_tiles * p.ci_tiles;
+  int splits = (device_sm_count() + units - 1) / units;
+  if (splits < 1) splits = 1;
+  if ((long long)splits > p.kblocks_total) splits = (int)p.kblocks_total;
+  p.splits = splits;
+  p.dw = dw;
+  p.Cout_pad = Cout_pad;
+  p.Cin_pad = Cin_pad;
+
+  CUtensorMap tmDY, tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)Cout_pad, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)Cout_pad * H * Wp * 2};
+    uint32_t box[4] = {(uint32_t)p.bx, (uint32_t)p.by, 128, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmDY, dy_cm, 4, dims, str, box, es, "wgrad dY")) return -1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)Cin_pad, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)Cin_pad * H * Wp * 2};
+    uint32_t box[4] = {(uint32_t)p.bx, (uint32_t)p.by, (uint32_t)block_n, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmX, x_cm, 4, dims, str, box, es, "wgrad X")) return -1;
+  }
+  if (block_n == 256) return launch_wgrad<256>(tmDY, tmX, p, stream);
+  if (block_n == 128) return launch_wgrad<128>(tmDY, tmX, p, stream);
+  return launch_wgrad<64>(tmDY, tmX, p, stream);
+}
+
+extern "C" int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream) {
+  DB_REQUIRE(x && y, "nhwc_to_cm: null pointer");
+  DB_REQUIRE(C % 32 == 0 && Wp % 8 == 0 && Wp >= W, "nhwc_to_cm: bad C=%d / Wp=%d", C, Wp);
+  const long long tiles = (long long)B * H * ((Wp + 31) / 32) * (C / 32);
+  nhwc_to_cm_f16_kernel<<<grid_cap(tiles * 256, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), B, H, W, C, Wp);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_relu_mask_f16(void* dy, const void* y, long long n, void* stream) {
+  DB_REQUIRE(dy && y && n > 0 && n % 8 == 0, "relu_mask: bad arguments");
+  relu_mask_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint4*>(dy), reinterpret_cast<const uint4*>(y), n / 8);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C,
+                                           void* stream) {
+  DB_REQUIRE(x && dy && dx && C % 8 == 0, "maxpool2_bwd: bad arguments");
+  const long long total = (long long)B * H * W * (C / 8);
+  maxpool2_bwd_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), B, H, W,
+      C / 8, H / 2, W / 2);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_upsample2_bwd_nhwc(const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
+  DB_REQUIRE(dy && dx && C % 8 == 0, "upsample2_bwd: bad arguments");
+  const long long total = (long long)B * H * W * (C / 8);
+  upsample2_bwd_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), B, H, W, C / 8);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_bias_grad(const void* dy, float* db, long long rows, int C, void* stream) {
+  DB_REQUIRE(dy && db && rows > 0 && C % 64 == 0, "bias_grad: bad arguments");
+  long long bx = (rows + 8 * 64 - 1) / (8 * 64);
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)(C / 64));
+  bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(dy), db, rows, C);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}

@@ -1,0 +1,432 @@
+"""B200-native DREAM networks: reference-compatible parameter trees + a layer plan executed by
+libdreamb200's tensor-core kernels.
+
+Reference: dream/models.py -- DreamHourglass (:557-827, vgg-Q / vgg-F), ResnetSimple (:17-155,
+resnet-H / resnet-F).  The modules here are NOT nn.Sequential stacks of torch ops: they hold fp32
+`nn.Parameter`s / BN buffers under exactly the reference's state-dict names (so released `.pth`
+files load, `torch.save` round-trips and torch optimizers update them in place), and
+`forward` runs a plan of C-ABI calls on NHWC fp16 activations:
+
+  first layer : dreamb200_im2col_first (patch gather fused with the fp32 NCHW -> fp16 NHWC pack)
+                + one 1-tap GEMM,
+  conv 3x3    : 9-tap implicit GEMM, bias+ReLU in the epilogue,
+  1x1 / s2    : 1-tap GEMM, TMA element stride 2 for strided layers,
+  BN (eval)   : folded into the packed fp16 weights + fp32 bias at pack time,
+  bottleneck  : residual add + ReLU fused in the epilogue of the block's last 1x1,
+  ConvTranspose k3s2p1op1 / k4s2p1 : 4 sub-pixel phases, each a small-tap conv writing an
+                interleaved (strided TMA store) view of the output -- no zero insertion,
+  head        : last conv writes fp32 NCHW belief maps directly.
+
+Packed weights are cached and re-packed only when a parameter's version counter changes.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+VGG_TRUNK = [
+    ("layer_0_1_down", (0, 2), 64),
+    ("layer_0_2_down", (5, 7), 128),
+    ("layer_0_3_down", (10, 12, 14, 16), 256),
+    ("layer_0_4_down", (19, 21, 23, 25), 512),
+    ("layer_0_5_down", (28, 30, 32, 34), 512),
+]
+RESNET101_BLOCKS = (3, 4, 23, 3)
+BN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter tree helpers
+# ----------------------------------------------------------------------------------------------
+class _Node(nn.Module):
+    """Container with no forward: only gives parameters their reference state-dict path."""
+
+
+def _node_for(root, dotted):
+    mod = root
+    parts = dotted.split(".")
+    for p in parts:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    return mod
+
+
+def _add_conv(root, key, cin, cout, k, bias=True, transposed=False):
+    n = _node_for(root, key)
+    shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    w = torch.empty(shape)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))          # nn.Conv2d / nn.ConvTranspose2d default
+    n.weight = nn.Parameter(w)
+    if bias:
+        fan_in = shape[1] * k * k
+        bound = 1.0 / math.sqrt(fan_in)
+        n.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+    else:
+        n.register_parameter("bias", None)
+
+
+def _add_bn(root, key, c):
+    n = _node_for(root, key)
+    n.weight = nn.Parameter(torch.ones(c))
+    n.bias = nn.Parameter(torch.zeros(c))
+    n.register_buffer("running_mean", torch.zeros(c))
+    n.register_buffer("running_var", torch.ones(c))
+    n.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+def _deconv_phase_taps(k, phase):
+    """ConvTranspose (stride 2, padding 1): output row 2*y'+phase receives kernel rows ky with
+    (phase + 1 - ky) even, from input row y' + (phase + 1 - ky) / 2."""
+    return [((phase + 1 - ky) // 2, ky) for ky in range(k) if (phase + 1 - ky) % 2 == 0]
+
+
+class _PackedConv:
+    """One plan step: packed fp16 weights + fp32 bias + tap list for dreamb200_conv2d_fwd."""
+    __slots__ = ("w", "b", "taps", "stride", "relu", "cout", "phases")
+
+    def __init__(self, w, b, taps, stride=1, relu=False, cout=None, phases=None):
+        self.w, self.b, self.taps, self.stride, self.relu, self.cout, self.phases = \
+            w, b, taps, stride, relu, cout, phases
+
+
+def _bn_scale_shift(bn, conv_bias):
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + BN_EPS)
+    base = conv_bias.detach().float() if conv_bias is not None else torch.zeros_like(scale)
+    shift = (base - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return scale, shift
+
+
+def _pack3x3(node, relu, bn=None, stride=1, cout_pad=None, cin_pad=None):
+    scale, bias = (None, node.bias)
+    if bn is not None:
+        scale, bias = _bn_scale_shift(bn, node.bias)
+    ksz = node.weight.shape[2]
+    rs = [(r, s) for r in range(ksz) for s in range(ksz)]
+    w = ops.pack_conv_weight(node.weight, rs, cin_pad=cin_pad, cout_pad=cout_pad, scale=scale)
+    taps = [(r - ksz // 2, s - ksz // 2) for r, s in rs]
+    return _PackedConv(w, ops.pad_bias(bias, w.shape[1], w.device), taps, stride=stride, relu=relu,
+                       cout=node.weight.shape[0])
+
+
+def _pack_deconv(node, k, relu, bn=None):
+    """ConvTranspose2d weight [Cin,Cout,k,k] -> 4 phase convs (py,px) with their own tap lists."""
+    scale, bias = (None, node.bias)
+    if bn is not None:
+        scale, bias = _bn_scale_shift(bn, node.bias)
+    w_oihw = node.weight.detach().permute(1, 0, 2, 3)            # -> [Cout,Cin,k,k]
+    cout = w_oihw.shape[0]
+    phases = []
+    for py in range(2):
+        for px in range(2):
+            ty, tx = _deconv_phase_taps(k, py), _deconv_phase_taps(k, px)
+            rs = [(ky, kx) for (_, ky) in ty for (_, kx) in tx]
+            taps = [(dy, dx) for (dy, _) in ty for (dx, _) in tx]
+            w = ops.pack_conv_weight(w_oihw, rs, scale=scale)
+            phases.append((py, px, w, taps))
+    b = ops.pad_bias(bias, ops.round_up(cout, 64), node.weight.device)
+    return _PackedConv(None, b, None, relu=relu, cout=cout, phases=phases)
+
+
+def _run_conv(pc, x, residual=None, head_cout=None, residual_f32=None, want_f32=False):
+    B, H, W, _ = x.shape
+    if pc.stride == 1:
+        Ho, Wo = H, W
+    else:
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1      # k=1/p=0 and k=3/p=1 give the same size
+    y_f32 = None
+    if want_f32:
+        y_f32 = torch.empty((B, Ho, Wo, pc.w.shape[1]), dtype=torch.float32, device=x.device)
+    y = ops.conv_taps(x, pc.w, pc.b, pc.taps, Ho, Wo, stride=pc.stride, relu=pc.relu, residual=residual,
+                      head_cout=head_cout, residual_f32=residual_f32, y_f32=y_f32)
+    return (y, y_f32) if want_f32 else y
+
+
+def _run_deconv(pc, x):
+    B, H, W, _ = x.shape
+    cpad = pc.b.numel()
+    Ho, Wo = 2 * H, 2 * W
+    y = torch.empty((B, Ho, Wo, cpad), dtype=torch.float16, device=x.device)
+    strides = (2 * cpad, 2 * Wo * cpad, Ho * Wo * cpad)
+    for py, px, w, taps in pc.phases:
+        ops.conv_taps(x, w, pc.b, taps, H, W, relu=pc.relu, y=y, y_strides=strides,
+                      y_offset=(py * Wo + px) * cpad)
+    return y
+
+
+class _PlanModule(nn.Module):
+    """Shared machinery: lazy weight packing keyed on parameter versions; eval-only in this round's
+    forward (training goes through dream_b200.autograd)."""
+
+    def __init__(self):
+        super().__init__()
+        self._plan = None
+        self._plan_key = None
+
+    def _version_key(self):
+        key = [self.training]
+        for t in list(self.parameters()) + list(self.buffers()):
+            key.append((t.data_ptr(), t._version))
+        return tuple(key)
+
+    def plan(self):
+        key = self._version_key()
+        if self._plan is None or key != self._plan_key:
+            with torch.no_grad():
+                self._plan = self._build_plan()
+            self._plan_key = key
+        return self._plan
+
+    def _check_input(self, x):
+        assert x.dim() == 4 and x.shape[1] == 3, "expected an RGB batch [B,3,H,W], got {}".format(tuple(x.shape))
+        if not x.is_cuda:
+            raise RuntimeError("dream_b200 runs on a CUDA device only (no CPU fallback); got a CPU tensor")
+        return x.contiguous().float()
+
+
+# ----------------------------------------------------------------------------------------------
+# DreamHourglass (vgg-Q / vgg-F)
+# ----------------------------------------------------------------------------------------------
+class DreamHourglass(_PlanModule):
+    """dream/models.py:557-827.  Same constructor keywords; `forward(x)` returns `[belief_maps]`
+    (plus the soft-argmax keypoints when `internalize_spatial_softmax`)."""
+
+    def __init__(self, n_keypoints, n_image_input_channels=3, internalize_spatial_softmax=True,
+                 learned_beta=True, initial_beta=1.0, skip_connections=False, deconv_decoder=False,
+                 full_output=False):
+        super().__init__()
+        assert n_image_input_channels == 3, "only RGB input is supported"
+        self.n_keypoints = n_keypoints
+        self.n_image_input_channels = n_image_input_channels
+        self.internalize_spatial_softmax = internalize_spatial_softmax
+        self.skip_connections = skip_connections
+        self.deconv_decoder = deconv_decoder
+        self.full_output = full_output
+        if internalize_spatial_softmax:
+            self.n_output_heads = 2
+            self.learned_beta = learned_beta
+            self.initial_beta = initial_beta
+        else:
+            self.n_output_heads = 1
+            self.learned_beta = False
+        cin = 3
+        for block, idxs, ch in VGG_TRUNK:
+            for j in idxs:
+                _add_conv(self, "%s.%d" % (block, j), cin, ch, 3)
+                cin = ch
+        if deconv_decoder:
+            for name, ci, co, with_conv in (("deconv_0_4", 512, 256, True), ("deconv_0_3", 256, 128, True),
+                                            ("deconv_0_2", 128, 64, True), ("deconv_0_1", 64, 64, False)):
+                _add_conv(self, name + ".0", ci, co, 3, transposed=True)
+                if with_conv:
+                    _add_conv(self, name + ".2", co, co, 3)
+        else:
+            _add_conv(self, "upsample_0_4.4", 512, 256, 3); _add_conv(self, "upsample_0_4.6", 256, 256, 3)
+            _add_conv(self, "upsample_0_3.4", 256, 128, 3); _add_conv(self, "upsample_0_3.6", 128, 64, 3)
+            if full_output:
+                for name in ("upsample_0_2", "upsample_0_1"):
+                    _add_conv(self, name + ".2", 64, 64, 3); _add_conv(self, name + ".4", 64, 64, 3)
+        _add_conv(self, "heads_0.0", 64, 64, 3)
+        _add_conv(self, "heads_0.2", 64, 32, 3)
+        _add_conv(self, "heads_0.4", 32, n_keypoints, 3)
+        if internalize_spatial_softmax:
+            from .spatial_softmax import SoftArgmaxPavlo
+            self.softmax = nn.Sequential()
+            self.softmax.add_module("0", SoftArgmaxPavlo(n_keypoints=n_keypoints, learned_beta=self.learned_beta,
+                                                         initial_beta=self.initial_beta))
+
+    def _n(self, key):
+        return _node_for(self, key)
+
+    def _build_plan(self):
+        P = {}
+        first = self._n("layer_0_1_down.0")
+        wf = ops.pack_first_weight(first.weight, 64)
+        P["first"] = _PackedConv(wf, ops.pad_bias(first.bias, 64, wf.device), [(0, 0)], relu=True, cout=64)
+        for block, idxs, _ in VGG_TRUNK:
+            for j in idxs:
+                if block == "layer_0_1_down" and j == 0:
+                    continue
+                P["%s.%d" % (block, j)] = _pack3x3(self._n("%s.%d" % (block, j)), relu=True)
+        if self.deconv_decoder:
+            for name in ("deconv_0_4", "deconv_0_3", "deconv_0_2", "deconv_0_1"):
+                P[name + ".0"] = _pack_deconv(self._n(name + ".0"), 3, relu=True)
+                if name != "deconv_0_1":
+                    P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
+        else:
+            for name in ("upsample_0_4", "upsample_0_3"):
+                P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)
+                P[name + ".6"] = _pack3x3(self._n(name + ".6"), relu=False)
+            if self.full_output:
+                for name in ("upsample_0_2", "upsample_0_1"):
+                    P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
+                    P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)
+        P["heads_0.0"] = _pack3x3(self._n("heads_0.0"), relu=True)
+        P["heads_0.2"] = _pack3x3(self._n("heads_0.2"), relu=True)            # 32 real + 32 zero channels
+        P["heads_0.4"] = _pack3x3(self._n("heads_0.4"), relu=False, cout_pad=16, cin_pad=64)
+        return P
+
+    def belief_maps(self, x):
+        """Inference forward: fp32 NCHW [B,3,H,W] (cuda) -> fp32 NCHW belief maps [B,K,h,w]."""
+        x = self._check_input(x)
+        P = self.plan()
+        t = ops.im2col_first(x, 3, 3, 1, 1, 64)
+        t = _run_conv(P["first"], t)
+        skips = {}
+        for bi, (block, idxs, _) in enumerate(VGG_TRUNK):
+            if bi > 0:
+                t = ops.maxpool(t, 2, 2, 0)
+                skips["pool%d" % bi] = t
+            for j in idxs:
+                if block == "layer_0_1_down" and j == 0:
+                    continue
+                t = _run_conv(P["%s.%d" % (block, j)], t)
+            skips[block] = t
+        sk = self.skip_connections
+        if sk:
+            t = ops.add_(t.clone(), skips["pool4"])
+        if self.deconv_decoder:
+            t = _run_conv(P["deconv_0_4.2"], _run_deconv(P["deconv_0_4.0"], t))
+            if sk:
+                t = ops.add_(t, skips["pool3"])
+            t = _run_conv(P["deconv_0_3.2"], _run_deconv(P["deconv_0_3.0"], t))
+            if sk:
+                t = ops.add_(t, skips["pool2"])
+            t = _run_conv(P["deconv_0_2.2"], _run_deconv(P["deconv_0_2.0"], t))
+            if sk:
+                t = ops.add_(t, skips["pool1"])
+            t = _run_deconv(P["deconv_0_1.0"], t)
+            if sk:
+                t = ops.add_(t, skips["layer_0_1_down"])
+        else:
+            t = _run_conv(P["upsample_0_4.6"], _run_conv(P["upsample_0_4.4"], ops.upsample2(t)))
+            if sk:
+                t = ops.add_(t, skips["pool3"])
+            t = _run_conv(P["upsample_0_3.6"], _run_conv(P["upsample_0_3.4"], ops.upsample2(t)))
+            if self.full_output:
+                for name in ("upsample_0_2", "upsample_0_1"):
+                    t = _run_conv(P[name + ".4"], _run_conv(P[name + ".2"], ops.upsample2(t)))
+        t = _run_conv(P["heads_0.0"], t)
+        t = _run_conv(P["heads_0.2"], t)
+        return _run_conv(P["heads_0.4"], t, head_cout=self.n_keypoints)
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            from .autograd import hourglass_train_forward
+            out = hourglass_train_forward(self, x)
+        else:
+            out = self.belief_maps(x)
+        outputs = [out]
+        if self.internalize_spatial_softmax:
+            outputs.append(self.softmax(out))
+        return outputs
+
+
+# ----------------------------------------------------------------------------------------------
+# ResnetSimple (resnet-H / resnet-F)
+# ----------------------------------------------------------------------------------------------
+class ResnetSimple(_PlanModule):
+    """dream/models.py:17-155: ResNet-101 trunk + 4 (H) or 5 (F) ConvTranspose(4,2,1)+BN+ReLU + 1x1 head."""
+
+    def __init__(self, n_keypoints=7, freeze=False, pretrained=True, full=False):
+        super().__init__()
+        self.full = full
+        self.n_keypoints = n_keypoints
+        _add_conv(self, "conv1", 3, 64, 7, bias=False)
+        _add_bn(self, "bn1", 64)
+        inplanes = 64
+        for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
+            planes = 64 * 2 ** (li - 1)
+            for bi in range(nblocks):
+                k = "layer%d.%d" % (li, bi)
+                _add_conv(self, k + ".conv1", inplanes, planes, 1, bias=False); _add_bn(self, k + ".bn1", planes)
+                _add_conv(self, k + ".conv2", planes, planes, 3, bias=False); _add_bn(self, k + ".bn2", planes)
+                _add_conv(self, k + ".conv3", planes, planes * 4, 1, bias=False); _add_bn(self, k + ".bn3", planes * 4)
+                if bi == 0:
+                    _add_conv(self, k + ".downsample.0", inplanes, planes * 4, 1, bias=False)
+                    _add_bn(self, k + ".downsample.1", planes * 4)
+                inplanes = planes * 4
+        cin = 2048
+        for i in range(4):
+            _add_conv(self, "upsample.%d" % (3 * i), cin, 256, 4, transposed=True)
+            _add_bn(self, "upsample.%d" % (3 * i + 1), 256)
+            cin = 256
+        if full:
+            _add_conv(self, "upsample2.0", 256, 256, 4, transposed=True)
+            _add_bn(self, "upsample2.1", 256)
+            _add_conv(self, "upsample2.3", 256, n_keypoints, 1)
+        else:
+            _add_conv(self, "upsample.12", 256, n_keypoints, 1)
+
+    def _n(self, key):
+        return _node_for(self, key)
+
+    def _build_plan(self):
+        P = {}
+        c1, b1 = self._n("conv1"), self._n("bn1")
+        scale, shift = _bn_scale_shift(b1, None)
+        wf = ops.pack_first_weight(c1.weight, 192, scale=scale)
+        P["conv1"] = _PackedConv(wf, ops.pad_bias(shift, 64, wf.device), [(0, 0)], relu=True, cout=64)
+        for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
+            for bi in range(nblocks):
+                k = "layer%d.%d" % (li, bi)
+                stride = 2 if (li > 1 and bi == 0) else 1
+                P[k + ".conv1"] = _pack3x3(self._n(k + ".conv1"), relu=True, bn=self._n(k + ".bn1"))
+                P[k + ".conv2"] = _pack3x3(self._n(k + ".conv2"), relu=True, bn=self._n(k + ".bn2"), stride=stride)
+                P[k + ".conv3"] = _pack3x3(self._n(k + ".conv3"), relu=True, bn=self._n(k + ".bn3"))
+                if bi == 0:
+                    P[k + ".down"] = _pack3x3(self._n(k + ".downsample.0"), relu=False,
+                                              bn=self._n(k + ".downsample.1"), stride=stride)
+        for i in range(4):
+            P["up%d" % i] = _pack_deconv(self._n("upsample.%d" % (3 * i)), 4, relu=True,
+                                         bn=self._n("upsample.%d" % (3 * i + 1)))
+        if self.full:
+            P["up4"] = _pack_deconv(self._n("upsample2.0"), 4, relu=True, bn=self._n("upsample2.1"))
+            P["head"] = _pack3x3(self._n("upsample2.3"), relu=False, cout_pad=16)
+        else:
+            P["head"] = _pack3x3(self._n("upsample.12"), relu=False, cout_pad=16)
+        return P
+
+    def belief_maps(self, x):
+        x = self._check_input(x)
+        P = self.plan()
+        t = ops.im2col_first(x, 7, 7, 2, 3, 192)
+        t = _run_conv(P["conv1"], t)
+        t = ops.maxpool(t, 3, 2, 1)
+        # The identity stream of the 33 bottlenecks stays fp32 (t32) next to the fp16 copy (t) that feeds
+        # the tensor cores: rounding the trunk to fp16 at every block random-walks past the 1e-3 gate.
+        t32 = None
+        for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
+            for bi in range(nblocks):
+                k = "layer%d.%d" % (li, bi)
+                idn32 = _run_conv(P[k + ".down"], t, want_f32=True)[1] if bi == 0 else t32
+                o = _run_conv(P[k + ".conv1"], t)
+                o = _run_conv(P[k + ".conv2"], o)
+                t, t32 = _run_conv(P[k + ".conv3"], o, residual_f32=idn32, want_f32=True)  # relu(bn3+identity)
+        for i in range(4):
+            t = _run_deconv(P["up%d" % i], t)
+        if self.full:
+            t = _run_deconv(P["up4"], t)
+        return _run_conv(P["head"], t, head_cout=self.n_keypoints)
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "ResnetSimple training (BatchNorm batch statistics + backward) is not built yet in "
+                "dream_b200; inference (eval mode / torch.no_grad()) is supported.")
+        return [self.belief_maps(x)]
+
+
+class DataParallelShim(nn.Module):
+    """Gives parameters the `module.` prefix torch.nn.DataParallel puts into the reference's
+    state dicts (dream/network.py:244-256,616) without DataParallel's per-forward replicate /
+    scatter / gather: multi-GPU is process-per-GPU in dream_b200 (see dream_b200/distributed.py)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

@@ -1,0 +1,402 @@
+"""`DreamNetwork` -- the drop-in facade (reference: dream/network.py:18-696).
+
+Same module-level names (`KNOWN_ARCHITECTURES`, `KNOWN_OPTIMIZERS`, `create_network_from_config_file`,
+`create_network_from_config_data`), same constructor validation (every `assert` of
+network.py:76-183 with its message), attributes and methods, so `scripts/train_network.py` and
+`scripts/network_inference_dataset.py` run against it unchanged.
+
+What differs underneath:
+  * `.model` is `DataParallelShim(DreamHourglass | ResnetSimple)` from dream_b200.models: fp32
+    parameters under the reference's `module.*` names, forward = hand-written sm_100a kernels.
+  * `inference` extracts keypoints on the device (dreamb200_peaks + a vectorised decision table)
+    with ONE device->host copy per batch instead of K*B `.cpu()` syncs (network.py:541-581,
+    image_proc.py:931-933).
+  * Multi-GPU is one process per GPU: `gpu_ids` selects this process's device (first id), and when
+    torch.distributed is initialised `train` all-reduces gradients over NCCL instead of
+    DataParallel's replicate/scatter/gather/reduce (network.py:244-256).
+There is no CPU path: without a CUDA device the constructor raises.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import image_proc
+from . import models
+from .spatial_softmax import SoftArgmaxPavlo  # noqa: F401  (same import surface as the reference)
+
+KNOWN_ARCHITECTURES = [
+    "vgg",
+    "resnet",
+]
+
+KNOWN_OPTIMIZERS = [
+    "adam",  # the Adam optimizer
+    "sgd",
+]  # the Stochastic Gradient Descent optimizer
+
+
+# ----------------------------------------------------------------------------------------------
+# YAML config I/O (the reference uses ruamel.yaml; fall back to PyYAML, incl. its `!!omap` files)
+# ----------------------------------------------------------------------------------------------
+def _omap_to_dict(node):
+    if isinstance(node, list) and node and all(isinstance(e, tuple) and len(e) == 2 for e in node):
+        return OrderedDict((k, _omap_to_dict(v)) for k, v in node)
+    if isinstance(node, dict):
+        return OrderedDict((k, _omap_to_dict(v)) for k, v in node.items())
+    if isinstance(node, list):
+        return [_omap_to_dict(e) for e in node]
+    return node
+
+
+def load_yaml_config(path):
+    try:
+        import ruamel.yaml
+        with open(path, "r") as f:
+            return ruamel.yaml.YAML(typ="safe").load(f)
+    except ImportError:
+        import yaml
+        with open(path, "r") as f:
+            return _omap_to_dict(yaml.safe_load(f))
+
+
+def _plain(node):
+    if isinstance(node, dict):
+        return {k: _plain(v) for k, v in node.items()}
+    if isinstance(node, (list, tuple)):
+        return [_plain(v) for v in node]
+    if isinstance(node, np.generic):
+        return node.item()
+    return node
+
+
+def dump_yaml_config(config, path):
+    try:
+        import ruamel.yaml
+        saver = ruamel.yaml.YAML()
+        saver.default_flow_style = False
+        saver.explicit_start = False
+        with open(path, "w") as f:
+            saver.dump(config, f)
+    except ImportError:
+        import yaml
+        with open(path, "w") as f:
+            yaml.safe_dump(_plain(config), f, default_flow_style=False, sort_keys=False)
+
+
+def create_network_from_config_file(config_file_path, network_params_path=None):
+    assert os.path.exists(config_file_path), \
+        'Expected config_file_path "{}" to exist, but it does not.'.format(config_file_path)
+    if network_params_path:
+        load_network_parameters = True
+        assert os.path.exists(network_params_path), \
+            'If provided, expected network_params_path "{}" to exist, but it does not.'.format(
+                network_params_path)
+    else:
+        load_network_parameters = False
+
+    print('Loading network config file "{}"'.format(config_file_path))
+    network_config = load_yaml_config(config_file_path)
+    dream_network = create_network_from_config_data(network_config)
+    if load_network_parameters:
+        print('Loading network weights file "{}"'.format(network_params_path))
+        dream_network.model.load_state_dict(torch.load(network_params_path, map_location="cpu"))
+    return dream_network
+
+
+def create_network_from_config_data(network_config_data):
+    return DreamNetwork(network_config_data)
+
+
+def _distributed_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+class DreamNetwork:
+    def __init__(self, network_config):
+        # ---- validation: same keys, same messages as dream/network.py:76-183 ----
+        assert "architecture" in network_config, \
+            'Required key "architecture" is missing from network configuration.'
+        assert "type" in network_config["architecture"], \
+            'Required key "type" in dictionary "architecture" is missing from network configuration.'
+        assert "manipulator" in network_config, \
+            'Required key "manipulator" is missing from network configuration.'
+        assert "name" in network_config["manipulator"], \
+            'Required key "name" in dictionary "manipulator" is missing from network configuration.'
+        assert "keypoints" in network_config["manipulator"], \
+            'Required key "keypoints" in dictionary "manipulator" is missing from network configuration.'
+
+        self.keypoint_names = []
+        self.friendly_keypoint_names = []
+        self.ros_keypoint_frames = []
+        for kp_def in network_config["manipulator"]["keypoints"]:
+            assert "name" in kp_def, 'Keypoint specification is missing key "name".'
+            kp_name = kp_def["name"]
+            self.keypoint_names.append(kp_name)
+            self.friendly_keypoint_names.append(kp_def["friendly_name"] if "friendly_name" in kp_def else kp_name)
+            self.ros_keypoint_frames.append(kp_def["ros_frame"] if "ros_frame" in kp_def else kp_name)
+
+        self.network_config = network_config
+        self.manipulator_name = self.network_config["manipulator"]["name"]
+        self.n_keypoints = len(self.keypoint_names)
+        self.architecture_type = self.network_config["architecture"]["type"]
+
+        print("`network.py`.  `DreamNetwork:__init()` ----------")
+        print("  Manipulator: {}".format(self.manipulator_name))
+        print("  Keypoint names: {}".format(self.keypoint_names))
+        print("  Friendly keypoint names: {}".format(self.friendly_keypoint_names))
+        print("  Architecture type: {}".format(self.architecture_type))
+
+        arch = self.network_config["architecture"]
+        assert "image_normalization" in arch, \
+            'Required key "image_normalization" in dictionary "architecture" is missing from network configuration.'
+        self.image_normalization = arch["image_normalization"]
+        assert "image_preprocessing" in arch, \
+            'Required key "image_preprocessing" in dictionary "architecture" is missing from network configuration.'
+        assert self.image_preprocessing() in image_proc.KNOWN_IMAGE_PREPROC_TYPES, \
+            'Image preprocessing type "{}" is not recognized.'.format(self.image_preprocessing())
+        assert "output_heads" in arch, \
+            'Required key "output_heads" in dictionary "architecture" is missing from network configuration.'
+        assert self.architecture_type in KNOWN_ARCHITECTURES, \
+            'Expected architecture type "{}" to be in the list of known network architectures, but it is not.'.format(
+                self.architecture_type)
+        assert "input_heads" in arch, \
+            'Required key "input_heads" in dictionary "architecture" is missing from network configuration.'
+        assert arch["input_heads"][0] == "image_rgb", 'First input head must be "image_rgb".'
+        assert "training" in self.network_config, 'Required key "training" is missing from network configuration.'
+        assert "config" in self.network_config["training"], \
+            'Required key "config" in dictionary "training" is missing from network configuration.'
+        assert "net_input_resolution" in self.network_config["training"]["config"], \
+            'Required key "net_input_resolution" is missing from training configuration.'
+        len_res = len(self.network_config["training"]["config"]["net_input_resolution"])
+        assert len_res == 2, \
+            "Expected trained net input resolution to have length 2, but it has length {}.".format(len_res)
+        assert "platform" in self.network_config["training"], \
+            'Required key "platform" in dictionary "training" is missing from network configuration.'
+        gpu_ids = self.network_config["training"]["platform"]["gpu_ids"]
+
+        # ---- device: one process per GPU ----
+        if not torch.cuda.is_available():
+            raise RuntimeError("dream_b200.DreamNetwork needs a CUDA (sm_100a) device; there is no CPU fallback.")
+        if _distributed_world() > 1 and "LOCAL_RANK" in os.environ:
+            dev_index = int(os.environ["LOCAL_RANK"])
+        elif gpu_ids:
+            dev_index = int(gpu_ids[0])
+        else:
+            dev_index = torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        torch.cuda.set_device(self.device)
+
+        self.use_belief_peak_scores = True
+        self.belief_peak_next_best_score = 0.25
+
+        # ---- model (dream/network.py:194-298) ----
+        if self.architecture_type == "vgg":
+            if "spatial_softmax" in arch:
+                assert arch["output_heads"] == ["belief_maps", "keypoints"]
+                vgg_kwargs = {
+                    "internalize_spatial_softmax": True,
+                    "learned_beta": arch["spatial_softmax"]["learned_beta"],
+                    "initial_beta": arch["spatial_softmax"]["initial_beta"],
+                }
+            else:
+                assert arch["output_heads"] == ["belief_maps"]
+                vgg_kwargs = {"internalize_spatial_softmax": False}
+            if "deconv_decoder" in arch and "full_output" not in arch:
+                vgg_kwargs["deconv_decoder"] = arch["deconv_decoder"]
+            elif "full_output" in arch:
+                vgg_kwargs["deconv_decoder"] = arch["deconv_decoder"]
+                vgg_kwargs["full_output"] = True
+            if "skip_connections" in arch:
+                vgg_kwargs["skip_connections"] = arch["skip_connections"]
+            if "n_stages" in arch:
+                raise NotImplementedError(
+                    "DreamHourglassMultiStage (architecture.n_stages, dream/models.py:350-553) is not built "
+                    "in dream_b200 yet; no shipped arch config uses it.")
+            net = models.DreamHourglass(self.n_keypoints, **vgg_kwargs)
+        elif self.architecture_type == "resnet":
+            assert arch["output_heads"] == ["belief_maps"]
+            resnet_kwargs = {}
+            if "full_decoder" in arch:
+                resnet_kwargs["full"] = arch["full_decoder"]
+            net = models.ResnetSimple(self.n_keypoints, **resnet_kwargs)
+        else:
+            assert False, 'Network architecture type "{}" not defined.'.format(self.architecture_type)
+        self.model = models.DataParallelShim(net).to(self.device)
+
+        loss_type = arch["loss"]["type"]
+        if loss_type == "mse":
+            self.criterion = torch.nn.MSELoss()
+        elif loss_type == "huber":
+            self.criterion = torch.nn.SmoothL1Loss()
+        else:
+            assert False, "Loss not yet implemented."
+
+        self.optimizer = None
+
+        # ---- output resolution by a dummy forward (network.py:304-317) ----
+        out_res = list(self.net_output_resolution_from_input_resolution(self.trained_net_input_resolution()))
+        if "net_output_resolution" in self.network_config["training"]["config"]:
+            assert self.network_config["training"]["config"]["net_output_resolution"] == out_res, \
+                "Network model and config file disagree for trained network output resolution."
+        else:
+            self.network_config["training"]["config"]["net_output_resolution"] = out_res
+
+    # ------------------------------------------------------------------------------------------
+    def trained_net_input_resolution(self):
+        return tuple(self.network_config["training"]["config"]["net_input_resolution"])
+
+    def trained_net_output_resolution(self):
+        return tuple(self.network_config["training"]["config"]["net_output_resolution"])
+
+    def image_preprocessing(self):
+        return self.network_config["architecture"]["image_preprocessing"]
+
+    def train(self, network_input_heads, target):
+        assert self.optimizer, "Optimizer must be defined. Use enable_training() first."
+        self.optimizer.zero_grad()
+        loss = self.loss(network_input_heads, target)
+        loss.backward()
+        if _distributed_world() > 1:
+            from .distributed import allreduce_gradients
+            allreduce_gradients(self.model)
+        self.optimizer.step()
+        return loss
+
+    def loss(self, network_input_heads, target):
+        network_output_heads = self.model(network_input_heads[0])
+        if self.network_config["architecture"]["output_heads"] == ["belief_maps"]:
+            if "n_stages" in self.network_config["architecture"]:
+                n_stages = len(network_output_heads)
+                expanded_size = [n_stages] + [-1] * target.dim()
+                loss = self.criterion(torch.stack(network_output_heads),
+                                      target.unsqueeze(0).expand(expanded_size))
+            else:
+                loss = self.criterion(network_output_heads[0], target)
+        else:
+            assert False, "Not yet implemented."
+        return loss
+
+    def net_resolutions_from_image_raw_resolution(self, image_raw_resolution, image_preprocessing_override=None):
+        assert len(image_raw_resolution) == 2, \
+            'Expected "image_raw_resolution" to have length 2, but it has length {}.'.format(
+                len(image_raw_resolution))
+        image_preprocessing = image_preprocessing_override if image_preprocessing_override \
+            else self.image_preprocessing()
+        net_input_resolution = image_proc.resolution_after_preprocessing(
+            image_raw_resolution, self.trained_net_input_resolution(), image_preprocessing)
+        return net_input_resolution, self.net_output_resolution_from_input_resolution(net_input_resolution)
+
+    def net_output_resolution_from_input_resolution(self, net_input_resolution):
+        assert len(net_input_resolution) == 2, \
+            'Expected "net_input_resolution" to have length 2, but it has length {}.'.format(
+                len(net_input_resolution))
+        netin_width, netin_height = net_input_resolution
+        with torch.no_grad():
+            x = torch.zeros(1, 3, netin_height, netin_width, device=self.device)
+            out = self.model(x)
+            shape = out[0][0].shape
+        return (shape[2], shape[1])
+
+    def keypoints_from_image(self, input_rgb_image_as_pil, image_preprocessing_override=None, debug=False):
+        from PIL import Image as PILImage
+        assert isinstance(input_rgb_image_as_pil, PILImage.Image), \
+            'Expected "input_rgb_image_as_pil" to be a PIL Image, but it is {}.'.format(
+                type(input_rgb_image_as_pil))
+        input_image_resolution = input_rgb_image_as_pil.size
+        image_preprocessing = image_preprocessing_override if image_preprocessing_override \
+            else self.image_preprocessing()
+        preproc = image_proc.preprocess_image(input_rgb_image_as_pil, self.trained_net_input_resolution(),
+                                              image_preprocessing)
+        netin_res_inf = preproc.size
+        # ToTensor + Normalize(mean, stdev) (network.py:449-459)
+        arr = np.asarray(preproc.convert("RGB"), dtype=np.float32) / 255.0
+        mean = np.asarray(self.image_normalization["mean"], dtype=np.float32)
+        std = np.asarray(self.image_normalization["stdev"], dtype=np.float32)
+        x = torch.from_numpy(np.ascontiguousarray(((arr - mean) / std).transpose(2, 0, 1)))
+        with torch.no_grad():
+            belief_batch, kp_batch = self.inference(x.unsqueeze(0).to(self.device))
+        belief_maps_net_out = belief_batch[0]
+        detected_kp_projs_net_out = np.array(kp_batch[0], dtype=float)
+        belief_map = belief_maps_net_out[0]
+        netout_res_inf = (belief_map.shape[1], belief_map.shape[0])
+        kp_net_in = image_proc.convert_keypoints_to_netin_from_netout(
+            detected_kp_projs_net_out, netout_res_inf, netin_res_inf)
+        kp_raw = image_proc.convert_keypoints_to_raw_from_netin(
+            kp_net_in, netin_res_inf, input_image_resolution, image_preprocessing)
+        detection_result = {"detected_keypoints": kp_raw}
+        if debug:
+            detection_result["image_rgb_net_input"] = preproc
+            detection_result["belief_maps"] = belief_maps_net_out
+            detection_result["detected_keypoints_net_output"] = detected_kp_projs_net_out
+            detection_result["detected_keypoints_net_input"] = kp_net_in
+        return detection_result
+
+    def inference(self, network_input):
+        output_heads = self.network_config["architecture"]["output_heads"]
+        if output_heads == ["belief_maps", "keypoints"]:
+            return self.model(network_input)
+        if output_heads == ["belief_maps"]:
+            belief_maps_batch = self.model(network_input)[-1]
+            tw, th = self.trained_net_output_resolution()
+            offset = 0.0 if (tw >= 400 and th >= 400) else 0.4395     # network.py:534-538
+            B, K = belief_maps_batch.shape[0], belief_maps_batch.shape[1]
+            table = image_proc.find_peaks_device(belief_maps_batch.detach(), offset)
+            if self.use_belief_peak_scores:
+                kps = image_proc.select_keypoints_device(table, self.belief_peak_next_best_score)
+            else:
+                one = table.counts == 1
+                kps = torch.full((table.n_maps, 2), -999.999, dtype=torch.float64, device=table.counts.device)
+                kps[one] = table.summary[one, :2]
+            detected_kp_projs_batch = kps.view(B, K, 2).cpu().float()
+            return [belief_maps_batch, detected_kp_projs_batch]
+        assert False, "Could not determine how to conduct inference on this network."
+
+    # ------------------------------------------------------------------------------------------
+    def save_network_config(self, config_file_path, overwrite=False):
+        if not overwrite:
+            assert not os.path.exists(config_file_path), \
+                'Output file already exists in "{}".'.format(config_file_path)
+        dump_yaml_config(self.network_config, config_file_path)
+
+    def save_network_params(self, network_params_path, overwrite=False):
+        if not overwrite:
+            assert not os.path.exists(network_params_path), \
+                'Output file already exists in "{}".'.format(network_params_path)
+        torch.save(self.model.state_dict(), network_params_path)
+
+    def save_network(self, output_dir, output_filename_without_extension, overwrite=False):
+        os.makedirs(output_dir, exist_ok=True)
+        self.save_network_config(os.path.join(output_dir, output_filename_without_extension + ".yaml"), overwrite)
+        self.save_network_params(os.path.join(output_dir, output_filename_without_extension + ".pth"), overwrite)
+
+    def enable_training(self):
+        if not self.optimizer:
+            cfg = self.network_config["training"]["config"]
+            assert "optimizer" in cfg, \
+                'Required key "optimizer" in dictionary "config" is missing from network configuration.'
+            assert "type" in cfg["optimizer"], \
+                'Required key "type" in dictionary "optimizer" is missing from network configuration.'
+            network_parameters = filter(lambda p: p.requires_grad, self.model.parameters())
+            optimizer_type = cfg["optimizer"]["type"]
+            assert optimizer_type in KNOWN_OPTIMIZERS, \
+                'Expected optimizer_type "{}" to be in the list of known optimizers, but it is not.'.format(
+                    optimizer_type)
+            if optimizer_type == "adam":
+                assert "learning_rate" in cfg["optimizer"], \
+                    'Required key "learning_rate" in dictionary "optimizer" is missing to use the Adam optimizer.'
+                self.optimizer = torch.optim.Adam(network_parameters, lr=cfg["optimizer"]["learning_rate"])
+            elif optimizer_type == "sgd":
+                assert "learning_rate" in cfg["optimizer"], \
+                    'Required key "learning_rate" in dictionary "optimizer" is missing to use the SGD optimizer.'
+                self.optimizer = torch.optim.SGD(network_parameters, lr=cfg["optimizer"]["learning_rate"])
+            else:
+                assert False, 'Optimizer "{}" is not defined.'.format(optimizer_type)
+        self.model.train()
+
+    def enable_evaluation(self):
+        self.model.eval()

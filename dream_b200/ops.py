@@ -11,6 +11,12 @@ from . import _lib
 from ._lib import ConvDesc, check, lib
 
 
+# Optional per-launch timing (bench.py / tools): when PROFILE is a list, every tensor-core conv
+# launch is bracketed by CUDA events on the launching stream and appended as
+# (tag, algorithmic_flops, start_event, end_event).  None (default) = zero overhead.
+PROFILE = None
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -24,7 +30,7 @@ def round_up(v, m):
 
 
 def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
-              y_strides=None, head_cout=None):
+              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None):
     """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
 
     x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
@@ -61,12 +67,25 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
             y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
         d.out_mode = _lib.OUT_NHWC_F16; d.cout_real = Cout_pad
         d.y_stride_w, d.y_stride_h, d.y_stride_b = y_strides
-    d.y = y.data_ptr() if not isinstance(y, int) else y
+    d.y = y.data_ptr() + y_offset * y.element_size()
     if residual is not None:
         assert residual.dtype == torch.float16 and residual.is_contiguous()
         assert tuple(residual.shape) == (B, Ho, Wo, Cout_pad)
         d.residual = residual.data_ptr()
     d.relu = 1 if relu else 0
+    for name, t in (("residual_f32", residual_f32), ("y_f32", y_f32)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, Ho, Wo, Cout_pad)
+            setattr(d, name, t.data_ptr())
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
+        e1.record()
+        block_n = 16 if head_cout is not None else (256 if Cout_pad % 256 == 0 else 128 if Cout_pad % 128 == 0 else 64)
+        tag = "conv_tc<%d> T%d Cin%d Cout%d %dx%d s%d" % (block_n, T, Cin, Cout_pad, Ho, Wo, stride)
+        PROFILE.append((tag, 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
+        return y
     check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
     return y
 
@@ -90,6 +109,14 @@ def maxpool(x, k, s, p):
     y = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
     check(lib().dreamb200_maxpool_nhwc(_ptr(x), _ptr(y), B, H, W_, Cc, k, s, p, Ho, Wo, _stream()),
           "dreamb200_maxpool_nhwc")
+    return y
+
+
+def add_(y, x):
+    """y += x in place (fp16, same shape)."""
+    assert y.dtype == torch.float16 and x.dtype == torch.float16 and y.shape == x.shape
+    assert y.is_contiguous() and x.is_contiguous()
+    check(lib().dreamb200_add_f16(_ptr(y), _ptr(x), y.numel(), _stream()), "dreamb200_add_f16")
     return y
 
 
@@ -157,3 +184,67 @@ def pad_bias(b, cout_pad, device):
     if b is not None:
         out[: b.numel()] = b.detach().float()
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# backward (training) wrappers
+# ----------------------------------------------------------------------------------------------
+def nhwc_to_cm(x):
+    """NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] with Wp = round_up(W, 8) (zero padded)."""
+    B, H, W_, Cc = x.shape
+    Wp = round_up(W_, 8)
+    y = torch.empty((B, Cc, H, Wp), dtype=torch.float16, device=x.device)
+    check(lib().dreamb200_nhwc_to_cm_f16(_ptr(x), _ptr(y), B, H, W_, Cc, Wp, _stream()), "dreamb200_nhwc_to_cm_f16")
+    return y
+
+
+def wgrad(dy, x, taps):
+    """dW[tap][co][ci] = sum_p dy[p][co] * x[p + tap][ci]; dy/x NHWC fp16 of equal H, W -> fp32 [T,Co,Ci]."""
+    B, H, W_, Co = dy.shape
+    Ci = x.shape[3]
+    assert tuple(x.shape[:3]) == (B, H, W_)
+    dy_cm = nhwc_to_cm(dy)
+    x_cm = nhwc_to_cm(x)
+    dw = torch.zeros((len(taps), Co, Ci), dtype=torch.float32, device=dy.device)
+    tdy = (C.c_int8 * len(taps))(*[t[0] for t in taps])
+    tdx = (C.c_int8 * len(taps))(*[t[1] for t in taps])
+    e0 = e1 = None
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().dreamb200_wgrad(_ptr(dy_cm), _ptr(x_cm), _ptr(dw), B, H, W_, dy_cm.shape[3], Co, Ci, len(taps),
+                                C.cast(tdy, C.c_void_p), C.cast(tdx, C.c_void_p), _stream()), "dreamb200_wgrad")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("wgrad_tc T%d Cin%d Cout%d %dx%d" % (len(taps), Ci, Co, H, W_),
+                        2.0 * B * H * W_ * Co * Ci * len(taps), e0, e1))
+    return dw
+
+
+def relu_mask_(dy, y):
+    assert dy.shape == y.shape and dy.dtype == torch.float16 and y.dtype == torch.float16
+    check(lib().dreamb200_relu_mask_f16(_ptr(dy), _ptr(y), dy.numel(), _stream()), "dreamb200_relu_mask_f16")
+    return dy
+
+
+def maxpool2_bwd(x, dy):
+    B, H, W_, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(lib().dreamb200_maxpool2_bwd_nhwc(_ptr(x), _ptr(dy), _ptr(dx), B, H, W_, Cc, _stream()),
+          "dreamb200_maxpool2_bwd_nhwc")
+    return dx
+
+
+def upsample2_bwd(dy):
+    B, H2, W2, Cc = dy.shape
+    dx = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=torch.float16, device=dy.device)
+    check(lib().dreamb200_upsample2_bwd_nhwc(_ptr(dy), _ptr(dx), B, H2 // 2, W2 // 2, Cc, _stream()),
+          "dreamb200_upsample2_bwd_nhwc")
+    return dx
+
+
+def bias_grad(dy):
+    Cc = dy.shape[-1]
+    db = torch.zeros((Cc,), dtype=torch.float32, device=dy.device)
+    check(lib().dreamb200_bias_grad(_ptr(dy), _ptr(db), dy.numel() // Cc, Cc, _stream()), "dreamb200_bias_grad")
+    return db

@@ -51,6 +51,11 @@ typedef struct dreamb200_conv_desc {
   /* fused epilogue */
   const void* residual;                     /* fp16 NHWC [B,Ho,Wo,Cout_pad] dense, or NULL */
   int32_t relu;
+  /* fp32 residual stream (ResNet identity path kept in fp32 across the 33 bottlenecks):
+     residual_f32 is added like `residual`; y_f32, when set, receives an fp32 NHWC dense copy
+     of the (post-ReLU) output next to the fp16 one. Both [B,Ho,Wo,Cout_pad] or NULL. */
+  const float* residual_f32;
+  float* y_f32;
 } dreamb200_conv_desc;
 
 const char* dreamb200_last_error(void);
@@ -67,6 +72,8 @@ int dreamb200_im2col_first(const float* x, void* out, int B, int H, int W,
 int dreamb200_maxpool_nhwc(const void* x, void* y, int B, int H, int W, int C,
                            int k, int s, int p, int Ho, int Wo, void* stream);
 int dreamb200_upsample2_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* y += x elementwise, fp16, n % 8 == 0 (hourglass skip connections, models.py:775-799) */
+int dreamb200_add_f16(void* y, const void* x, long long n, void* stream);
 /* fp16 NHWC [B,H,W,Cpad] -> fp32 NCHW [B,C,H,W] and back (debug / boundary) */
 int dreamb200_nhwc_f16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int Cpad, int C, void* stream);
 int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int H, int W, int C, int Cpad, void* stream);
@@ -79,6 +86,24 @@ int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int H, int W,
 int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
                     double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
+
+/* ---- backward (training) ------------------------------------------------------------------ */
+/* NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp % 8 == 0, pad columns zeroed): operand
+   layout of dreamb200_wgrad */
+int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream);
+/* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy_cm/x_cm channel-major fp16 (above),
+   dw fp32 [taps][Cout_pad][Cin_pad] (caller zeroes it); autograd of nn.Conv2d weights */
+int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, int B, int H, int W, int Wp,
+                    int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                    void* stream);
+/* dy *= (y > 0): autograd of nn.ReLU given its output */
+int dreamb200_relu_mask_f16(void* dy, const void* y, long long n, void* stream);
+/* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C] */
+int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* autograd of nn.Upsample(scale_factor=2): dy [B,2H,2W,C] -> dx [B,H,W,C] */
+int dreamb200_upsample2_bwd_nhwc(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* db[c] += sum_rows dy[row][c]; dy fp16 [rows,C], C % 64 == 0 (caller zeroes db) */
+int dreamb200_bias_grad(const void* dy, float* db, long long rows, int C, void* stream);
 
 int dreamb200_softargmax(const float* maps, const float* beta, float* out_xy,
                          int B, int K, int H, int W, float* scratch, void* stream);

@@ -57,37 +57,45 @@ def main():
     torch.set_num_threads(8)
 
     # ---------------- networks ----------------
+    # name -> (constructor, shape table, input shape, weight mode).  "default" = the reference's own
+    # initialisation statistics (the 1e-3 gate); "he" = stress weights (see ref_models).
+    V = ref_models.vgg_state_shapes
+    R = ref_models.resnet_state_shapes
+    HG = models.DreamHourglass
     nets = {
-        "vgg_q": (lambda: models.DreamHourglass(7, internalize_spatial_softmax=False),
-                  ref_models.vgg_state_shapes(7, prefix=""), (2, 3, 64, 80), 0.1),
-        "vgg_f": (lambda: models.DreamHourglass(7, internalize_spatial_softmax=False, deconv_decoder=True,
-                                                full_output=True),
-                  ref_models.vgg_state_shapes(7, deconv_decoder=True, full_output=True, prefix=""),
-                  (2, 3, 48, 64), 0.1),
-        "vgg_q_skip": (lambda: models.DreamHourglass(7, internalize_spatial_softmax=False, skip_connections=True),
-                       ref_models.vgg_state_shapes(7, prefix=""), (1, 3, 64, 64), 0.1),
-        "vgg_q_full": (lambda: models.DreamHourglass(7, internalize_spatial_softmax=False, full_output=True),
-                       ref_models.vgg_state_shapes(7, full_output=True, prefix=""), (1, 3, 48, 48), 0.1),
-        "resnet_h": (lambda: models.ResnetSimple(7, pretrained=False), ref_models.resnet_state_shapes(7, prefix=""),
-                     (2, 3, 96, 80), 0.04),
-        "resnet_f": (lambda: models.ResnetSimple(7, pretrained=False, full=True),
-                     ref_models.resnet_state_shapes(7, full=True, prefix=""), (1, 3, 72, 104), 0.04),
+        "vgg_q": (lambda: HG(7, internalize_spatial_softmax=False), V(7, prefix=""), (2, 3, 64, 80), "default"),
+        "vgg_q_he": (lambda: HG(7, internalize_spatial_softmax=False), V(7, prefix=""), (2, 3, 64, 80), "he"),
+        "vgg_f": (lambda: HG(7, internalize_spatial_softmax=False, deconv_decoder=True, full_output=True),
+                  V(7, deconv_decoder=True, full_output=True, prefix=""), (2, 3, 48, 64), "default"),
+        "vgg_f_he": (lambda: HG(7, internalize_spatial_softmax=False, deconv_decoder=True, full_output=True),
+                     V(7, deconv_decoder=True, full_output=True, prefix=""), (1, 3, 48, 64), "he"),
+        "vgg_q_skip": (lambda: HG(7, internalize_spatial_softmax=False, skip_connections=True),
+                       V(7, prefix=""), (1, 3, 64, 64), "default"),
+        "vgg_q_full": (lambda: HG(7, internalize_spatial_softmax=False, full_output=True),
+                       V(7, full_output=True, prefix=""), (1, 3, 48, 48), "default"),
+        "resnet_h_he": (lambda: models.ResnetSimple(7, pretrained=False), R(7, prefix=""), (2, 3, 96, 80), "he"),
+        "resnet_f_he": (lambda: models.ResnetSimple(7, pretrained=False, full=True), R(7, full=True, prefix=""),
+                        (1, 3, 72, 104), "he"),
     }
-    for name, (ctor, shapes, xshape, gain) in nets.items():
+    for name, (ctor, shapes, xshape, mode) in nets.items():
         net = ctor().eval()
         ref_sd = net.state_dict()
         assert {k: tuple(v.shape) for k, v in ref_sd.items()} == {k: tuple(s) for k, s in shapes.items()}, \
             "oracle shape table disagrees with the reference module for " + name
         assert list(ref_sd.keys()) == list(shapes.keys()), "key order differs for " + name
-        sd = ref_models.synth_state_dict(shapes, seed=0, out_gain=gain)
-        net.load_state_dict(sd)
         g = torch.Generator().manual_seed(42)
         x = torch.rand(xshape, generator=g) * 2 - 1
+        # choose the output gain so the belief maps peak at ~1 like a trained network's
+        net.load_state_dict(ref_models.synth_state_dict(shapes, seed=0, out_gain=1.0, mode=mode))
+        with torch.no_grad():
+            gain = float(np.float32(1.0 / net(x)[0].abs().max().item()))
+        sd = ref_models.synth_state_dict(shapes, seed=0, out_gain=gain, mode=mode)
+        net.load_state_dict(sd)
         with torch.no_grad():
             y = net(x)[0]
-        out = {"x": x.numpy(), "y": y.numpy(), "gain": np.float64(gain)}
-        if name in ("vgg_q", "resnet_h"):
-            # gradients of an MSE loss (network.py:350-359) w.r.t. a few parameters + the input-side layer
+        out = {"x": x.numpy(), "y": y.numpy(), "gain": np.float64(gain), "mode": np.array(mode)}
+        if name in ("vgg_q", "vgg_q_he", "resnet_h_he"):
+            # gradients of an MSE loss (network.py:350-359) w.r.t. a few parameters
             net.train()                      # BN uses batch statistics in training (resnet)
             net.zero_grad()
             tg = torch.rand(y.shape, generator=g)
@@ -96,15 +104,14 @@ def main():
             loss.backward()
             out["target"] = tg.numpy()
             out["loss"] = np.float64(loss.item())
-            out["y_train"] = yt.detach().numpy()
             params = dict(net.named_parameters())
             picks = [k for k in params if k.endswith("weight")]
             picks = [picks[0], picks[1], picks[len(picks) // 2], picks[-2], picks[-1]]
             for k in picks:
-                out["grad::" + k] = params[k].grad.numpy()
-            out["grad_norms"] = np.array([params[k].grad.norm().item() for k in params])
+                gk = params[k].grad.numpy()
+                out["grad::" + k] = gk if gk.size <= 100000 else gk[:4]     # leading slice keeps fixtures small
         np.savez_compressed(os.path.join(GOLD, "net_%s.npz" % name), **out)
-        print(name, tuple(y.shape), float(y.abs().max()), float(y.std()))
+        print(name, mode, tuple(y.shape), "gain %.4g" % gain, float(y.abs().max()), float(y.std()))
 
     # ---------------- peaks ----------------
     rng = np.random.default_rng(7)

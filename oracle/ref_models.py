@@ -210,15 +210,29 @@ def _is_deconv_key(key):
     return False
 
 
-def synth_state_dict(shapes, seed=0, out_gain=1.0):
-    """Deterministic synthetic weights: each tensor is drawn from its own generator seeded by
-    crc32(key)+seed, He-scaled so activations stay O(1) through the network.  Used on both sides of
-    every parity test (reference here, oracle and CUDA path everywhere) so weights never need to be
-    stored.  `out_gain` scales the last conv so belief maps reach O(1) like a trained network."""
+def synth_state_dict(shapes, seed=0, out_gain=1.0, mode="he"):
+    """Deterministic synthetic weights; each tensor is drawn from its own generator seeded by
+    crc32(key)+seed, so both sides of every parity test can regenerate them from key names alone
+    (weights are never stored).  `out_gain` scales the last conv (weight and bias) so belief maps reach
+    O(1) like a trained network's.
+
+    mode="default": the statistics the reference's own constructors give a vgg network when nothing is
+        downloaded: VGG-19 trunk convs kaiming-normal(fan_out, relu) with zero bias
+        (torchvision vgg init), every freshly added conv / deconv (models.py:591-599, 618-747) PyTorch's
+        default kaiming-uniform(a=sqrt 5) weight and U(+-1/sqrt(fan_in)) bias.
+    mode="he": stress weights -- every conv He-scaled (std sqrt(2/fan_in)) so activations stay O(1)
+        through all layers and no bias path dominates; the worst case for 11-bit MMA operands.
+        BatchNorm: gamma U(0.8,1.2) (x0.25 on bn3 to keep the residual trunk O(1)), beta/mean N(0,0.05^2),
+        running_var U(0.75,1.25).
+    """
+    import math
     sd = {}
     last = [k for k in shapes if k.endswith(".weight") and len(shapes[k]) == 4][-1]
+    last_bias = last[:-len("weight")] + "bias"
     for key, shape in shapes.items():
         g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        k = key.split("module.")[-1]
+        vgg_trunk = k.startswith("layer_0_") and not k.startswith("layer_0_1_down.0.")
         if key.endswith("num_batches_tracked"):
             sd[key] = torch.zeros((), dtype=torch.long)
         elif key.endswith("running_var"):
@@ -226,16 +240,58 @@ def synth_state_dict(shapes, seed=0, out_gain=1.0):
         elif key.endswith("running_mean"):
             sd[key] = torch.randn(shape, generator=g) * 0.05
         elif len(shape) == 1 and key.endswith(".weight"):      # BN gamma
-            gain = 0.25 if key.endswith("bn3.weight") else 1.0  # keep the residual trunk O(1)
+            gain = 0.25 if key.endswith("bn3.weight") else 1.0
             sd[key] = (torch.rand(shape, generator=g) * 0.4 + 0.8) * gain
-        elif len(shape) == 1:                                   # bias / BN beta
-            sd[key] = torch.randn(shape, generator=g) * 0.05
-        else:
-            if _is_deconv_key(key):   # [Cin,Cout,k,k]; an output pixel sees k*k/4 taps per input channel
-                fan_in = shape[0] * (shape[2] * shape[3]) / 4.0
+        elif len(shape) == 1:                                   # conv bias / BN beta
+            wkey = key[:-len("bias")] + "weight"
+            if mode == "default" and len(shapes.get(wkey, ())) == 4:
+                if vgg_trunk:
+                    sd[key] = torch.zeros(shape)
+                else:
+                    ws = shapes[wkey]
+                    bound = 1.0 / math.sqrt(ws[1] * ws[2] * ws[3])
+                    sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
             else:
-                fan_in = shape[1] * shape[2] * shape[3]
-            sd[key] = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
-            if key == last:
-                sd[key] = sd[key] * out_gain
+                sd[key] = torch.randn(shape, generator=g) * 0.05
+        else:
+            if mode == "default":
+                if vgg_trunk:
+                    std = math.sqrt(2.0 / (shape[0] * shape[2] * shape[3]))          # fan_out
+                    sd[key] = torch.randn(shape, generator=g) * std
+                else:
+                    bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])           # torch's fan_in
+                    sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            else:
+                if _is_deconv_key(key):   # [Cin,Cout,k,k]; an output pixel sees k*k/4 taps per input channel
+                    fan_in = shape[0] * (shape[2] * shape[3]) / 4.0
+                else:
+                    fan_in = shape[1] * shape[2] * shape[3]
+                sd[key] = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+    sd[last] = sd[last] * out_gain
+    if last_bias in sd:
+        sd[last_bias] = sd[last_bias] * out_gain
     return sd
+
+
+class fp16_operands:
+    """Context manager (test infrastructure): evaluates the oracle with every conv / deconv operand
+    (activation and weight) rounded to fp16 and fp32 accumulation -- the reference algorithm as seen
+    through the tensor cores' 11-bit-significand input format.  Differences between the CUDA path and
+    THIS are implementation error; differences between this and the fp32 oracle are the operand format."""
+
+    def __enter__(self):
+        self._c, self._d = F.conv2d, F.conv_transpose2d
+        c, d = self._c, self._d
+
+        def conv2d(x, w, b=None, stride=1, padding=0):
+            return c(x.half().float(), w.half().float(), b, stride=stride, padding=padding)
+
+        def conv_transpose2d(x, w, b=None, stride=1, padding=0, output_padding=0):
+            return d(x.half().float(), w.half().float(), b, stride=stride, padding=padding,
+                     output_padding=output_padding)
+        F.conv2d, F.conv_transpose2d = conv2d, conv_transpose2d
+        return self
+
+    def __exit__(self, *exc):
+        F.conv2d, F.conv_transpose2d = self._c, self._d
+        return False

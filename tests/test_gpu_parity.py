@@ -1,0 +1,218 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C-ABI against the
+oracle restatement and the committed reference golden vectors.
+
+Tolerances (BASELINE.json north_star): belief maps within 1e-3 max-abs of the CPU fp32 path at
+trained-network scale (maps peaking near 1); integer peak coordinates bit-exact; refined (x, y)
+within 1e-3 px (we in fact require exact equality with the reference fixture).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_models, ref_peaks  # noqa: E402  (checker only)
+
+NETS = {   # fixture -> (family, constructor / forward kwargs)
+    "vgg_q": ("vgg", {}),
+    "vgg_q_he": ("vgg", {}),
+    "vgg_f": ("vgg", dict(deconv_decoder=True, full_output=True)),
+    "vgg_f_he": ("vgg", dict(deconv_decoder=True, full_output=True)),
+    "vgg_q_skip": ("vgg", dict(skip_connections=True)),
+    "vgg_q_full": ("vgg", dict(full_output=True)),
+    "resnet_h_he": ("resnet", dict(full=False)),
+    "resnet_f_he": ("resnet", dict(full=True)),
+}
+# Gates.  (1) BELIEF_TOL = 1e-3 max-abs against the fp32 reference on belief maps scaled to peak at 1, with the
+# reference's own initialisation statistics -- the north_star gate.  (2) "he" stress weights keep
+# every layer's activations O(1) with no bias path to hide behind: there the 11-bit significand of ANY
+# tensor-core operand format (fp16, and TF32 alike) costs ~1.1e-3 by itself (CPU emulation in
+# oracle.ref_models.fp16_operands), so the CUDA path is gated at EMU_TOL against that emulation -- i.e. it must be
+# the reference algorithm on fp16-rounded operands and nothing else -- and at STRESS_TOL against fp32.
+BELIEF_TOL = 1e-3
+EMU_TOL = 5e-4
+STRESS_TOL = 2.5e-3
+
+
+def _shapes(name):
+    kind, kw = NETS[name]
+    if kind == "vgg":
+        return ref_models.vgg_state_shapes(7, deconv_decoder=kw.get("deconv_decoder", False),
+                                           full_output=kw.get("full_output", False), prefix="")
+    return ref_models.resnet_state_shapes(7, full=kw["full"], prefix="")
+
+
+def _build(name, sd):
+    from dream_b200 import models
+    kind, kw = NETS[name]
+    if kind == "vgg":
+        net = models.DreamHourglass(7, internalize_spatial_softmax=False, **kw)
+    else:
+        net = models.ResnetSimple(7, **kw)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+def _oracle(name, sd, x, emulate=False):
+    kind, kw = NETS[name]
+    with torch.no_grad():
+        if emulate:
+            with ref_models.fp16_operands():
+                return _oracle(name, sd, x)
+        if kind == "vgg":
+            return ref_models.vgg_forward(sd, x, prefix="", **kw)
+        return ref_models.resnet_forward(sd, x, prefix="", **kw)
+
+
+@pytest.mark.parametrize("name", sorted(NETS))
+def test_network_forward_matches_reference_golden(name, golden_dir, built_lib):
+    g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+    mode = str(g["mode"])
+    sd = ref_models.synth_state_dict(_shapes(name), seed=0, out_gain=float(g["gain"]), mode=mode)
+    net = _build(name, sd)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        y = net(x.cuda())[0].cpu().numpy()
+    assert y.shape == g["y"].shape
+    err = np.abs(y - g["y"]).max()
+    emu = _oracle(name, sd, x, emulate=True).numpy()
+    err_emu = np.abs(y - emu).max()
+    print("%s [%s weights] max-abs vs reference fp32 golden %.3g, vs fp16-operand emulation %.3g (ref max %.3g)"
+          % (name, mode, err, err_emu, np.abs(g["y"]).max()))
+    assert err_emu <= EMU_TOL
+    assert err <= (BELIEF_TOL if mode == "default" else STRESS_TOL)
+
+
+@pytest.mark.parametrize("name,shape,mode", [
+    ("vgg_q", (3, 3, 400, 400), "default"), ("vgg_q", (1, 3, 400, 533), "default"),
+    ("vgg_f", (1, 3, 200, 200), "default"), ("vgg_q", (2, 3, 37, 53), "default"),
+    ("vgg_q_he", (2, 3, 400, 400), "he"),
+    ("resnet_h_he", (2, 3, 400, 400), "he"), ("resnet_f_he", (1, 3, 480, 640), "he")])
+def test_network_forward_matches_oracle_fullres(name, shape, mode, built_lib):
+    """BASELINE.json resolutions (400x400, shrink 533x400, 640x480) and an odd tiny size."""
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    sd = ref_models.synth_state_dict(_shapes(name), seed=1, mode=mode)
+    gain = 1.0 / _oracle(name, sd, x[:1]).abs().max().item()
+    sd = ref_models.synth_state_dict(_shapes(name), seed=1, out_gain=gain, mode=mode)
+    net = _build(name, sd)
+    ref = _oracle(name, sd, x).numpy()
+    emu = _oracle(name, sd, x, emulate=True).numpy()
+    with torch.no_grad():
+        y = net(x.cuda())[0].cpu().numpy()
+    assert y.shape == ref.shape
+    err, err_emu = np.abs(y - ref).max(), np.abs(y - emu).max()
+    print("%s %s [%s] max-abs vs fp32 oracle %.3g, vs fp16-operand emulation %.3g (ref max %.3g)"
+          % (name, shape, mode, err, err_emu, np.abs(ref).max()))
+    scale = max(1.0, np.abs(ref).max())
+    assert err_emu <= EMU_TOL * scale
+    assert err <= (BELIEF_TOL if mode == "default" else STRESS_TOL) * scale
+
+
+def test_state_dict_round_trip_with_module_prefix(built_lib):
+    from dream_b200 import models
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=2)
+    m = models.DataParallelShim(models.DreamHourglass(7, internalize_spatial_softmax=False))
+    m.load_state_dict(sd, strict=True)
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(out[k].cpu(), sd[k])
+    sdr = ref_models.synth_state_dict(ref_models.resnet_state_shapes(7, full=True), seed=2)
+    mr = models.DataParallelShim(models.ResnetSimple(7, full=True))
+    mr.load_state_dict(sdr, strict=True)
+    assert list(mr.state_dict().keys()) == list(sdr.keys())
+
+
+def _flat(peaks):
+    return np.array([(j, p[0], p[1], float(p[2]), p[3]) for j, lst in enumerate(peaks) for p in lst],
+                    dtype=np.float64).reshape(-1, 5)
+
+
+def test_peaks_kernel_matches_reference_golden(golden_dir, built_lib):
+    from dream_b200 import image_proc
+    g = np.load(os.path.join(golden_dir, "peaks.npz"))
+    names = sorted({k.split("::")[0] for k in g.files})
+    for name in names:
+        maps = torch.from_numpy(g[name + "::maps"]).cuda()
+        for off in (0.0, 0.4395):
+            ref = g["%s::peaks@%g" % (name, off)]
+            got = _flat(image_proc.peaks_from_belief_maps(maps, off))
+            assert got.shape == ref.shape, (name, off, got.shape, ref.shape)
+            assert np.array_equal(got[:, [0, 3, 4]], ref[:, [0, 3, 4]]), (name, off)
+            assert np.array_equal(got[:, 1:3], ref[:, 1:3]), (name, off, np.abs(got[:, 1:3] - ref[:, 1:3]).max())
+
+
+def test_peaks_kernel_integer_peaks_and_selection_match_oracle(built_lib):
+    """Random smooth-ish maps at the BASELINE batch shape: integer peaks bit-exact, decisions identical."""
+    from dream_b200 import image_proc
+    rng = np.random.default_rng(11)
+    B, K, H, W = 16, 7, 100, 100
+    maps = np.zeros((B * K, H, W), np.float32)
+    for i in range(B * K):
+        pts = [(rng.uniform(0, W), rng.uniform(0, H)) for _ in range(int(rng.integers(0, 4)))]
+        if pts:
+            amp = rng.uniform(0.2, 1.0, size=len(pts))
+            maps[i] = (ref_peaks.create_belief_map((W, H), pts) * amp[:, None, None]).sum(0)
+        maps[i] += rng.standard_normal((H, W)).astype(np.float32) * 0.01
+    table = image_proc.find_peaks_device(torch.from_numpy(maps).cuda(), 0.4395)
+    sel = image_proc.select_keypoints_device(table, 0.25).cpu().numpy()
+    counts = table.counts.cpu().numpy()
+    ij = table.ij.cpu().numpy()
+    ref = ref_peaks.peaks_from_belief_maps(maps, 0.4395)
+    ref_sel = np.array(ref_peaks.select_keypoints(ref))
+    for i in range(B * K):
+        assert counts[i] == len(ref[i]), i
+        sm = ref_peaks.gaussian_filter_f32(maps[i])
+        ys, xs = np.nonzero(ref_peaks.peak_mask(sm))
+        assert np.array_equal(ij[i, :counts[i], 0], xs) and np.array_equal(ij[i, :counts[i], 1], ys), i
+    assert np.array_equal(sel, ref_sel)
+
+
+def test_softargmax_kernel_matches_reference_golden(golden_dir, built_lib):
+    from dream_b200.spatial_softmax import SoftArgmaxPavlo
+    g = np.load(os.path.join(golden_dir, "softargmax.npz"))
+    sa = SoftArgmaxPavlo(n_keypoints=7, learned_beta=True, initial_beta=25.0).cuda()
+    with torch.no_grad():
+        sa.beta.copy_(torch.from_numpy(g["beta"]))
+        xy = sa(torch.from_numpy(g["maps"]).cuda()).cpu().numpy()
+    assert np.abs(xy - g["xy"]).max() <= 1e-3
+
+
+def test_facade_inference_end_to_end(built_lib):
+    """DreamNetwork.inference: belief maps + keypoints vs oracle restatement of network.py:503-590."""
+    from conftest import panda_config
+    from dream_b200 import network
+    net = network.create_network_from_config_data(panda_config("vgg"))
+    assert net.trained_net_output_resolution() == (100, 100)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=3, out_gain=13.0, mode="default")
+    net.model.load_state_dict(sd)
+    net.enable_evaluation()
+    x = torch.rand((2, 3, 400, 400), generator=torch.Generator().manual_seed(9)) * 2 - 1
+    with torch.no_grad():
+        belief, kps = net.inference(x.cuda())
+    assert tuple(belief.shape) == (2, 7, 100, 100) and belief.is_cuda
+    assert tuple(kps.shape) == (2, 7, 2) and not kps.is_cuda and kps.dtype == torch.float32
+    ref_maps = ref_models.vgg_forward(sd, x).detach().numpy()
+    assert np.abs(belief.cpu().numpy() - ref_maps).max() <= BELIEF_TOL * max(1.0, np.abs(ref_maps).max())
+    # keypoint decisions on OUR maps must equal the reference algorithm applied to the same maps
+    for b in range(2):
+        ref_k = ref_peaks.select_keypoints(ref_peaks.peaks_from_belief_maps(belief[b].cpu().numpy(), 0.4395))
+        assert np.array_equal(np.array(ref_k, dtype=np.float32), kps[b].numpy())
+
+
+def test_conv_rejects_bad_arguments(built_lib):
+    from dream_b200 import ops
+    from dream_b200._lib import DreamB200Error
+    x = torch.zeros((1, 8, 8, 64), dtype=torch.float16, device="cuda")
+    w = torch.zeros((1, 32, 64), dtype=torch.float16, device="cuda")       # Cout_pad not a multiple of 64
+    with pytest.raises(DreamB200Error):
+        ops.conv_taps(x, w, None, [(0, 0)], 8, 8)
+
+
+def test_missing_cpu_fallback_is_loud(built_lib):
+    from dream_b200 import models
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False).eval()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 32, 32))

@@ -1,0 +1,145 @@
+"""CPU: host-side logic of the drop-in (no GPU compute): C-ABI symbols, config handling, resolution
+arithmetic (reference test/test_image_proc.py:20-91 expectations), tap tables, plan bookkeeping."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_capi_exports_every_declared_symbol(built_lib):
+    from dream_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "dreamb200.h")).read()
+    declared = set(re.findall(r"\b(dreamb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(built_lib)
+    for sym in declared:
+        assert hasattr(lib, sym), "libdreamb200.so does not export " + sym
+    assert declared == set(_lib.DECLARED_SYMBOLS), declared ^ set(_lib.DECLARED_SYMBOLS)
+    assert _lib.lib().dreamb200_version() >= 100
+
+
+def test_conv_descriptor_layout_matches_header():
+    from dream_b200._lib import ConvDesc
+    # int8[16] x2 tap tables, pointer-aligned fields: catches drift between the ctypes mirror and the C struct
+    assert ConvDesc.tap_dy.offset + 16 == ConvDesc.tap_dx.offset
+    assert ctypes.sizeof(ConvDesc) % 8 == 0
+    assert ConvDesc.y.offset % 8 == 0 and ConvDesc.residual.offset % 8 == 0
+
+
+def test_shrink_and_crop_resolution_reference_expectations():
+    from dream_b200 import image_proc
+    # test/test_image_proc.py:20-91: (640,480) -> shrink (533,400); crop (480,480)@(80,0)
+    assert image_proc.shrink_resolution((640, 480), (400, 400)) == (533, 400)
+    assert image_proc.shrink_and_crop_resolution((640, 480), (400, 400)) == ((480, 480), (80, 0))
+    assert image_proc.resolution_after_preprocessing((640, 480), (400, 400), "none") == (640, 480)
+    assert image_proc.resolution_after_preprocessing((640, 480), (400, 400), "resize") == (400, 400)
+    assert image_proc.resolution_after_preprocessing((640, 480), (400, 400), "shrink") == (533, 400)
+    assert image_proc.resolution_after_preprocessing((640, 480), (400, 400), "shrink-and-crop") == (400, 400)
+    with pytest.raises(AssertionError):
+        image_proc.resolution_after_preprocessing((640, 480), (400, 400), "bogus")
+
+
+def test_keypoint_frame_round_trips():
+    from dream_b200 import image_proc
+    kp = np.array([[10.0, 20.0], [55.5, 70.25]])
+    for mode in image_proc.KNOWN_IMAGE_PREPROC_TYPES:
+        netin_res = image_proc.resolution_after_preprocessing((640, 480), (400, 400), mode)
+        a = image_proc.convert_keypoints_to_netin_from_raw(kp, (640, 480), netin_res, mode)
+        b = image_proc.convert_keypoints_to_raw_from_netin(a, netin_res, (640, 480), mode)
+        assert np.allclose(b, kp)
+    out = image_proc.convert_keypoints_to_netin_from_netout(np.array([[50.0, 25.0]]), (100, 100), (400, 400))
+    assert np.allclose(out, [[200.0, 100.0]])
+
+
+def test_create_belief_map_matches_oracle():
+    from dream_b200 import image_proc
+    from oracle import ref_peaks
+    pts = [(65.0, 20.0), (100.0, 80.0), (2.0, 2.0), (30.7, 40.2)]
+    assert np.array_equal(image_proc.create_belief_map((80, 60), pts), ref_peaks.create_belief_map((80, 60), pts))
+
+
+def test_gaussian_taps_match_oracle():
+    from dream_b200 import image_proc
+    from oracle import ref_peaks
+    w, r = image_proc.gaussian_half_kernel()
+    w2, r2 = ref_peaks.gaussian_weights()
+    assert r == r2 == 12 and np.array_equal(w, w2)
+
+
+def test_deconv_phase_taps_reproduce_conv_transpose():
+    """The sub-pixel decomposition used for ConvTranspose2d (k3 s2 p1 op1 and k4 s2 p1) is exact."""
+    from dream_b200.models import _deconv_phase_taps
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    for k, op in ((3, 1), (4, 0)):
+        x = torch.randn((1, 5, 6, 7), generator=g)
+        w = torch.randn((5, 4, k, k), generator=g)
+        ref = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=op)
+        out = torch.zeros_like(ref)
+        H, W = x.shape[2:]
+        assert ref.shape[2:] == (2 * H, 2 * W)
+        xp = F.pad(x, (2, 2, 2, 2))
+        for py in range(2):
+            for px in range(2):
+                acc = torch.zeros((1, 4, H, W))
+                for dy, ky in _deconv_phase_taps(k, py):
+                    for dx, kx in _deconv_phase_taps(k, px):
+                        patch = xp[:, :, 2 + dy:2 + dy + H, 2 + dx:2 + dx + W]
+                        acc += torch.einsum("bchw,co->bohw", patch, w[:, :, ky, kx])
+                out[:, :, py::2, px::2] = acc
+        assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_parameter_trees_have_reference_keys():
+    from dream_b200 import models
+    from oracle import ref_models
+    m = models.DataParallelShim(models.DreamHourglass(7, internalize_spatial_softmax=False))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+        {k: tuple(s) for k, s in ref_models.vgg_state_shapes(7).items()}
+    m = models.DataParallelShim(models.DreamHourglass(7, internalize_spatial_softmax=False, deconv_decoder=True,
+                                                      full_output=True))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+        {k: tuple(s) for k, s in ref_models.vgg_state_shapes(7, True, True).items()}
+    for full in (False, True):
+        m = models.DataParallelShim(models.ResnetSimple(7, full=full))
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+            {k: tuple(s) for k, s in ref_models.resnet_state_shapes(7, full=full).items()}
+    n_params = sum(p.numel() for p in models.DreamHourglass(7, internalize_spatial_softmax=False).parameters())
+    assert n_params == 22220615
+
+
+def test_facade_validation_messages_without_gpu():
+    from conftest import panda_config
+    from dream_b200 import network
+    cfg = panda_config()
+    del cfg["architecture"]["type"]
+    with pytest.raises(AssertionError, match='Required key "type"'):
+        network.DreamNetwork(cfg)
+    cfg = panda_config()
+    cfg["architecture"]["type"] = "alexnet"
+    with pytest.raises(AssertionError, match="known network architectures"):
+        network.DreamNetwork(cfg)
+    cfg = panda_config()
+    cfg["training"]["config"]["net_input_resolution"] = [400]
+    with pytest.raises(AssertionError, match="length 2"):
+        network.DreamNetwork(cfg)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            network.DreamNetwork(panda_config())
+
+
+def test_yaml_omap_loading(tmp_path):
+    from dream_b200 import network
+    p = tmp_path / "arch.yaml"
+    p.write_text("!!omap\n- architecture: !!omap\n  - type: vgg\n  - input_heads:\n    - image_rgb\n"
+                 "- training: !!omap\n  - config: !!omap\n    - net_input_resolution: [400, 400]\n")
+    cfg = network.load_yaml_config(str(p))
+    assert cfg["architecture"]["type"] == "vgg"
+    assert cfg["training"]["config"]["net_input_resolution"] == [400, 400]
+    out = tmp_path / "out.yaml"
+    network.dump_yaml_config(cfg, str(out))
+    assert network.load_yaml_config(str(out))["architecture"]["input_heads"] == ["image_rgb"]
