@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "dreamb200.h"
 
+#include <stdlib.h>
+
 namespace db200 {
 
 int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
@@ -353,6 +355,10 @@ extern "C" int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, i
     const int by = 64 / bx;
     const long tiles = (long)((W + bx - 1) / bx) * ((H + by - 1) / by);
     if (best < 0 || tiles < best) { best = tiles; p.bx = bx; p.by = by; }
+  }
+  if (const char* force = getenv("DREAMB200_WGRAD_BX")) {   // bring-up override: force the patch width
+    const int bx = atoi(force);
+    if (bx == 8 || bx == 16 || bx == 32 || bx == 64) { p.bx = bx; p.by = 64 / bx; }
   }
   p.px_tiles = (W + p.bx - 1) / p.bx;
   p.py_tiles = (H + p.by - 1) / p.by;

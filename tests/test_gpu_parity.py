@@ -28,12 +28,15 @@ NETS = {   # fixture -> (family, constructor / forward kwargs)
 # Gates.  (1) BELIEF_TOL = 1e-3 max-abs against the fp32 reference on belief maps scaled to peak at 1, with the
 # reference's own initialisation statistics -- the north_star gate.  (2) "he" stress weights keep
 # every layer's activations O(1) with no bias path to hide behind: there the 11-bit significand of ANY
-# tensor-core operand format (fp16, and TF32 alike) costs ~1.1e-3 by itself (CPU emulation in
-# oracle.ref_models.fp16_operands), so the CUDA path is gated at EMU_TOL against that emulation -- i.e. it must be
-# the reference algorithm on fp16-rounded operands and nothing else -- and at STRESS_TOL against fp32.
+# tensor-core operand format (fp16, and TF32 alike) costs 1.1e-3 .. 1.7e-3 by itself (CPU emulation
+# oracle.ref_models.fp16_operands; two such emulations that differ only in accumulation order already sit that
+# far apart after ~8 layers, because 1-ulp rounding flips cascade).  There the CUDA path must (a) stay within
+# STRESS_TOL of fp32 and (b) be no further from fp32 than FLOOR_FACTOR x the emulation is, i.e. sit AT the
+# operand format's noise floor.  Kernel exactness proper (one layer, same fp16 operands, error <= one fp16
+# output ulp) is test_single_layers_are_exact_up_to_output_rounding.
 BELIEF_TOL = 1e-3
-EMU_TOL = 5e-4
 STRESS_TOL = 2.5e-3
+FLOOR_FACTOR = 1.5
 
 
 def _shapes(name):
@@ -81,8 +84,9 @@ def test_network_forward_matches_reference_golden(name, golden_dir, built_lib):
     err_emu = np.abs(y - emu).max()
     print("%s [%s weights] max-abs vs reference fp32 golden %.3g, vs fp16-operand emulation %.3g (ref max %.3g)"
           % (name, mode, err, err_emu, np.abs(g["y"]).max()))
-    assert err_emu <= EMU_TOL
+    floor = np.abs(emu - g["y"]).max()
     assert err <= (BELIEF_TOL if mode == "default" else STRESS_TOL)
+    assert err <= FLOOR_FACTOR * floor + 1e-4, (err, floor)
 
 
 @pytest.mark.parametrize("name,shape,mode", [
@@ -106,8 +110,48 @@ def test_network_forward_matches_oracle_fullres(name, shape, mode, built_lib):
     print("%s %s [%s] max-abs vs fp32 oracle %.3g, vs fp16-operand emulation %.3g (ref max %.3g)"
           % (name, shape, mode, err, err_emu, np.abs(ref).max()))
     scale = max(1.0, np.abs(ref).max())
-    assert err_emu <= EMU_TOL * scale
+    floor = np.abs(emu - ref).max()
     assert err <= (BELIEF_TOL if mode == "default" else STRESS_TOL) * scale
+    assert err <= FLOOR_FACTOR * floor + 1e-4 * scale, (err, floor)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ksz,stride,extra", [
+    (2, 32, 32, 64, 64, 3, 1, ""), (2, 40, 40, 64, 128, 3, 1, ""), (2, 25, 25, 128, 256, 3, 1, ""),
+    (2, 50, 50, 256, 512, 3, 1, ""), (4, 25, 25, 512, 512, 3, 1, ""), (2, 100, 100, 64, 64, 3, 1, "res"),
+    (2, 100, 100, 64, 7, 3, 1, "head"), (2, 50, 50, 256, 64, 1, 1, ""), (2, 50, 50, 128, 128, 3, 2, ""),
+    (2, 25, 25, 256, 512, 1, 2, ""), (1, 13, 13, 2048, 256, 1, 1, "")])
+def test_single_layers_are_exact_up_to_output_rounding(B, H, W, Cin, Cout, ksz, stride, extra, built_lib):
+    """One conv layer on identical fp16 operands vs an fp32 conv: error <= one fp16 ulp of the output
+    (the store rounding) + fp32 accumulation noise; the fp32 head output must agree to 1e-5 relative."""
+    import torch.nn.functional as F
+    from dream_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = (torch.randn((B, H, W, Cin), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((Cout, Cin, ksz, ksz), device="cuda", generator=g) * (1.0 / (Cin * ksz * ksz) ** 0.5)
+    b = torch.randn((Cout,), device="cuda", generator=g) * 0.1
+    pad = ksz // 2
+    Ho, Wo = (H + 2 * pad - ksz) // stride + 1, (W + 2 * pad - ksz) // stride + 1
+    rs = [(r, s) for r in range(ksz) for s in range(ksz)]
+    taps = [(r - pad, s - pad) for r, s in rs]
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.half().double(), b.double(), stride=stride, padding=pad).float()
+    if extra == "head":
+        wp = ops.pack_conv_weight(w, rs, cout_pad=16)
+        got = ops.conv_taps(x, wp, ops.pad_bias(b, 16, "cuda"), taps, Ho, Wo, head_cout=Cout)
+        assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+        return
+    wp = ops.pack_conv_weight(w, rs)
+    residual = None
+    if extra == "res":
+        residual = torch.randn((B, Ho, Wo, wp.shape[1]), device="cuda", generator=g).half()
+        ref = F.relu(ref + residual[..., :Cout].permute(0, 3, 1, 2).float())
+    y = ops.conv_taps(x, wp, ops.pad_bias(b, wp.shape[1], "cuda"), taps, Ho, Wo, stride=stride,
+                      relu=(extra == "res"), residual=residual)
+    got = y[..., :Cout].permute(0, 3, 1, 2).float()
+    tol = ref.abs() * 2.0 ** -11 + 1e-5 * ref.abs().max()
+    assert bool(((got - ref).abs() <= tol).all()), ((got - ref).abs() - tol).max().item()
+    if wp.shape[1] > Cout:
+        assert float(y[..., Cout:].abs().max()) == 0.0          # padded channels stay exactly zero
 
 
 def test_state_dict_round_trip_with_module_prefix(built_lib):
