@@ -208,6 +208,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B       [61,64)
   return d;
 }
+// MN-major operand, SWIZZLE_128B: the tile is [K rows][64 MN elements = 128 B]; 8 K-rows form a
+// 1024 B group (SBO), the next 64 MN elements live `mn_chunk_bytes` further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((mn_chunk_bytes >> 4) & 0x3FFF) << 16;  // LBO: stride between 64-element MN chunks
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // SBO: stride between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// same as umma_idesc_f16_m128 but both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_m128_mn(uint32_t n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 // Instruction descriptor kind::f16: fp16 A/B (K-major), fp32 D, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_f16_m128(uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);

@@ -16,8 +16,6 @@
 #include "common.cuh"
 #include "dreamb200.h"
 
-#include <stdlib.h>
-
 namespace db200 {
 
 int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
@@ -28,31 +26,37 @@ int device_sm_count();
 // ---------------------------------------------------------------------------------------------
 // wgrad on tcgen05
 // ---------------------------------------------------------------------------------------------
+// k-block = one 16x8 pixel tile of one image (128 pixels = 8 MMAs of K=16).  Both operands are MN-major:
+//   A (dY): 2 boxes [128 px][64 co]  -> M = 128 output channels (a half-empty tile is TMA zero fill)
+//   B (X) : BLOCK_N/64 boxes [128 px][64 ci] fetched at the tap-shifted coordinates -> N = BLOCK_N
+// (a channel-major staging was tried first: a one-pixel x shift would need a 2-byte-granular TMA start
+//  address, which TMA does not allow -- shifts must be along non-contiguous dimensions, as they are in NHWC).
 struct WgradParams {
-  int B, H, W;              // activation extent (dY and X have the same H x W: stride-1 'same' convs)
-  int bx, by;               // pixel patch per k-block (bx*by == 64)
-  int px_tiles, py_tiles;   // patches per image
+  int B, H, W;
+  int tiles_x, tiles_y;
   int taps;
   int8_t dy[DREAMB200_MAX_TAPS], dx[DREAMB200_MAX_TAPS];
-  int co_tiles, ci_tiles;   // 128-row output tiles, BLOCK_N-column tiles
-  int splits;               // split-K factor
-  long long kblocks_total;  // B * py_tiles * px_tiles
+  int co_tiles, ci_tiles;
+  int splits;
+  long long kblocks_total;  // B * tiles_y * tiles_x
   float* dw;                // fp32 [taps][Cout_pad][Cin_pad], accumulated with atomics
   int Cout_pad, Cin_pad;
   int stages;
 };
 
 constexpr int kWgThreads = 192;
+constexpr int kWgTw = 16, kWgTh = 8;
+constexpr int kChunkBytes = 128 * 128;   // [128 px][64 ch] fp16
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgradParams p) {
-  constexpr int kABytes = 128 * 128;
-  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kABytes = 2 * kChunkBytes;
+  constexpr int kBBytes = (BLOCK_N / 64) * kChunkBytes;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
-  constexpr uint32_t kIdesc = umma_idesc_f16_m128(BLOCK_N);
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128_mn(BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -96,17 +100,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int patches = p.px_tiles * p.py_tiles;
+      const int tiles = p.tiles_x * p.tiles_y;
       for (long long kb = kb_lo; kb < kb_hi; ++kb) {
-        const int b = (int)(kb / patches);
-        const int r = (int)(kb - (long long)b * patches);
-        const int ty = r / p.px_tiles, tx = r - ty * p.px_tiles;
-        const int x0 = tx * p.bx, y0 = ty * p.by;
+        const int b = (int)(kb / tiles);
+        const int r = (int)(kb - (long long)b * tiles);
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * kWgTw, y0 = ty * kWgTh;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * kStageBytes;
         mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
-        tma_load_4d(sa, &tmDY, full_bar(stage), x0, y0, co_t * 128, b);
-        tma_load_4d(sa + kABytes, &tmX, full_bar(stage), x0 + p.dx[tap], y0 + p.dy[tap], ci_t * BLOCK_N, b);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, x0, y0, b);
+#pragma unroll
+        for (int n = 0; n < BLOCK_N / 64; ++n)
+          tma_load_4d(sa + kABytes + n * kChunkBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64,
+                      x0 + p.dx[tap], y0 + p.dy[tap], b);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -119,11 +128,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * kStageBytes;
-        const uint64_t adesc = umma_desc_k_sw128(sa);
-        const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+        const uint64_t adesc = umma_desc_mn_sw128(sa, kChunkBytes);
+        const uint64_t bdesc = umma_desc_mn_sw128(sa + kABytes, kChunkBytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // 16 pixel rows (2 KB) per MMA
+          umma_f16(tmem_base, adesc + 128u * k, bdesc + 128u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(empty_bar(stage));
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
@@ -158,9 +167,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 
 template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradParams& p, cudaStream_t stream) {
-  constexpr int kStageBytes = 128 * 128 + BLOCK_N * 128;
+  constexpr int kStageBytes = (2 + BLOCK_N / 64) * kChunkBytes;
   int stages = (232448 - 1024 - 512) / kStageBytes;
-  if (stages > 8) stages = 8;
+  if (stages > 6) stages = 6;
   p.stages = stages;
   const int smem_bytes = 1024 + stages * kStageBytes + 512;
   auto kern = wgrad_tc_kernel<BLOCK_N>;
@@ -337,38 +346,26 @@ static int grid_cap(long long work, int threads) {
 
 using namespace db200;
 
-extern "C" int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, int B, int H, int W, int Wp,
-                               int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
-                               void* stream_v) {
+extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
+                               int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
-  DB_REQUIRE(dy_cm && x_cm && dw && tap_dy && tap_dx, "wgrad: null pointer");
-  DB_REQUIRE(Wp % 8 == 0 && Wp >= W, "wgrad: row pitch Wp=%d must be a multiple of 8 and >= W", Wp);
-  DB_REQUIRE(Cout_pad % 64 == 0, "wgrad: Cout_pad=%d must be a multiple of 64", Cout_pad);
-  DB_REQUIRE(Cin_pad % 64 == 0, "wgrad: Cin_pad=%d must be a multiple of 64", Cin_pad);
+  DB_REQUIRE(dy && x && dw && tap_dy && tap_dx, "wgrad: null pointer");
+  DB_REQUIRE(Cout_pad % 64 == 0 && Cin_pad % 64 == 0, "wgrad: channel counts must be multiples of 64 (%d, %d)",
+             Cout_pad, Cin_pad);
   DB_REQUIRE(taps >= 1 && taps <= DREAMB200_MAX_TAPS, "wgrad: taps=%d out of range", taps);
+  DB_REQUIRE(B > 0 && H > 0 && W > 0, "wgrad: empty input");
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;
-  // patch shape: bx in {8,16,32,64}, the one that wastes the fewest padded pixels
-  long best = -1;
-  for (int bx = 8; bx <= 64; bx *= 2) {
-    const int by = 64 / bx;
-    const long tiles = (long)((W + bx - 1) / bx) * ((H + by - 1) / by);
-    if (best < 0 || tiles < best) { best = tiles; p.bx = bx; p.by = by; }
-  }
-  if (const char* force = getenv("DREAMB200_WGRAD_BX")) {   // bring-up override: force the patch width
-    const int bx = atoi(force);
-    if (bx == 8 || bx == 16 || bx == 32 || bx == 64) { p.bx = bx; p.by = 64 / bx; }
-  }
-  p.px_tiles = (W + p.bx - 1) / p.bx;
-  p.py_tiles = (H + p.by - 1) / p.by;
+  p.tiles_x = (W + kWgTw - 1) / kWgTw;
+  p.tiles_y = (H + kWgTh - 1) / kWgTh;
   p.taps = taps;
   memcpy(p.dy, tap_dy, taps);
   memcpy(p.dx, tap_dx, taps);
-  const int block_n = Cin_pad % 256 == 0 ? 256 : Cin_pad % 128 == 0 ? 128 : 64;
+  const int block_n = Cin_pad % 128 == 0 ? 128 : 64;
   p.co_tiles = (Cout_pad + 127) / 128;   // a half-empty last tile is zero-filled by TMA
   p.ci_tiles = Cin_pad / block_n;
-  p.kblocks_total = (long long)B * p.px_tiles * p.py_tiles;
+  p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
   const int units = taps * p.co_tiles * p.ci_tiles;
   int splits = (device_sm_count() + units - 1) / units;
   if (splits < 1) splits = 1;
@@ -379,21 +376,18 @@ extern "C" int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, i
   p.Cin_pad = Cin_pad;
 
   CUtensorMap tmDY, tmX;
+  const uint32_t box[4] = {64, kWgTw, kWgTh, 1};
+  const uint32_t es[4] = {1, 1, 1, 1};
   {
-    uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)Cout_pad, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)Cout_pad * H * Wp * 2};
-    uint32_t box[4] = {(uint32_t)p.bx, (uint32_t)p.by, 128, 1};
-    uint32_t es[4] = {1, 1, 1, 1};
-    if (make_tensor_map_f16(&tmDY, dy_cm, 4, dims, str, box, es, "wgrad dY")) return -1;
+    uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cout_pad * 2, (uint64_t)W * Cout_pad * 2, (uint64_t)H * W * Cout_pad * 2};
+    if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad dY")) return -1;
   }
   {
-    uint64_t dims[4] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)Cin_pad, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Wp * 2, (uint64_t)H * Wp * 2, (uint64_t)Cin_pad * H * Wp * 2};
-    uint32_t box[4] = {(uint32_t)p.bx, (uint32_t)p.by, (uint32_t)block_n, 1};
-    uint32_t es[4] = {1, 1, 1, 1};
-    if (make_tensor_map_f16(&tmX, x_cm, 4, dims, str, box, es, "wgrad X")) return -1;
+    uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
+    if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad X")) return -1;
   }
-  if (block_n == 256) return launch_wgrad<256>(tmDY, tmX, p, stream);
   if (block_n == 128) return launch_wgrad<128>(tmDY, tmX, p, stream);
   return launch_wgrad<64>(tmDY, tmX, p, stream);
 }

@@ -130,6 +130,34 @@ def _pack_deconv(node, k, relu, bn=None):
     return _PackedConv(None, b, None, relu=relu, cout=cout, phases=phases)
 
 
+def _pack_upsampled_conv(node, relu):
+    """nn.Upsample(scale_factor=2) (nearest) followed by a 3x3 'same' conv (models.py:691-697,703-709),
+    folded: output pixel (2y'+py, 2x'+px) reads up[2y'+py+r-1] = in[(2y'+py+r-1)//2], so the three kernel
+    rows collapse onto two input rows per phase ((r) -> dy: py=0: {0:-1, 1:0, 2:0}; py=1: {0:0, 1:0, 2:+1})
+    and likewise for columns.  Each of the 4 output phases is a 2x2-tap conv on the LOW-resolution input with
+    weights pre-summed in fp32 -- 4/9 of the MACs and no upsampled tensor in HBM."""
+    w = node.weight.detach().float()                      # [Cout, Cin, 3, 3]
+    cout = w.shape[0]
+    rows = {0: {-1: [0], 0: [1, 2]}, 1: {0: [0, 1], 1: [2]}}
+    phases = []
+    for py in range(2):
+        for px in range(2):
+            mats, taps = [], []
+            for dy, rr in rows[py].items():
+                for dx, ss in rows[px].items():
+                    acc = torch.zeros_like(w[:, :, 0, 0])
+                    for r in rr:
+                        for s_ in ss:
+                            acc = acc + w[:, :, r, s_]
+                    mats.append(acc)
+                    taps.append((dy, dx))
+            w4 = torch.stack(mats, dim=-1).unsqueeze(-1)                 # [Cout, Cin, T, 1] -> taps along dim 2
+            packed = ops.pack_conv_weight(w4, [(t, 0) for t in range(len(taps))])
+            phases.append((py, px, packed, taps))
+    b = ops.pad_bias(node.bias, ops.round_up(cout, 64), node.weight.device)
+    return _PackedConv(None, b, None, relu=relu, cout=cout, phases=phases)
+
+
 def _run_conv(pc, x, residual=None, head_cout=None, residual_f32=None, want_f32=False):
     B, H, W, _ = x.shape
     if pc.stride == 1:
@@ -257,11 +285,13 @@ class DreamHourglass(_PlanModule):
                     P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
         else:
             for name in ("upsample_0_4", "upsample_0_3"):
-                P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)
+                P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)          # training tape
+                P[name + ".4/up"] = _pack_upsampled_conv(self._n(name + ".4"), relu=True)   # inference
                 P[name + ".6"] = _pack3x3(self._n(name + ".6"), relu=False)
             if self.full_output:
                 for name in ("upsample_0_2", "upsample_0_1"):
                     P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
+                    P[name + ".2/up"] = _pack_upsampled_conv(self._n(name + ".2"), relu=True)
                     P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)
         P["heads_0.0"] = _pack3x3(self._n("heads_0.0"), relu=True)
         P["heads_0.2"] = _pack3x3(self._n("heads_0.2"), relu=True)            # 32 real + 32 zero channels
@@ -272,8 +302,7 @@ class DreamHourglass(_PlanModule):
         """Inference forward: fp32 NCHW [B,3,H,W] (cuda) -> fp32 NCHW belief maps [B,K,h,w]."""
         x = self._check_input(x)
         P = self.plan()
-        t = ops.im2col_first(x, 3, 3, 1, 1, 64)
-        t = _run_conv(P["first"], t)
+        t = ops.first_conv3x3(x, P["first"].w, P["first"].b)      # gather + pack + conv + bias + ReLU fused
         skips = {}
         for bi, (block, idxs, _) in enumerate(VGG_TRUNK):
             if bi > 0:
@@ -301,13 +330,14 @@ class DreamHourglass(_PlanModule):
             if sk:
                 t = ops.add_(t, skips["layer_0_1_down"])
         else:
-            t = _run_conv(P["upsample_0_4.6"], _run_conv(P["upsample_0_4.4"], ops.upsample2(t)))
+            # upsample x2 + conv folded into 4 phase convs on the low-res tensor (_pack_upsampled_conv)
+            t = _run_conv(P["upsample_0_4.6"], _run_deconv(P["upsample_0_4.4/up"], t))
             if sk:
                 t = ops.add_(t, skips["pool3"])
-            t = _run_conv(P["upsample_0_3.6"], _run_conv(P["upsample_0_3.4"], ops.upsample2(t)))
+            t = _run_conv(P["upsample_0_3.6"], _run_deconv(P["upsample_0_3.4/up"], t))
             if self.full_output:
                 for name in ("upsample_0_2", "upsample_0_1"):
-                    t = _run_conv(P[name + ".4"], _run_conv(P[name + ".2"], ops.upsample2(t)))
+                    t = _run_conv(P[name + ".4"], _run_deconv(P[name + ".2/up"], t))
         t = _run_conv(P["heads_0.0"], t)
         t = _run_conv(P["heads_0.2"], t)
         return _run_conv(P["heads_0.4"], t, head_cout=self.n_keypoints)

@@ -90,6 +90,24 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
     return y
 
 
+def first_conv3x3(x, w, bias):
+    """Fused first layer: fp32 NCHW [B,3,H,W] -> relu(conv3x3(x)+bias) as fp16 NHWC [B,H,W,64]."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+    assert tuple(w.shape) == (1, 64, 64) and w.dtype == torch.float16 and bias.numel() >= 64
+    B, _, H, W_ = x.shape
+    y = torch.empty((B, H, W_, 64), dtype=torch.float16, device=x.device)
+    e0 = e1 = None
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().dreamb200_first_conv3x3(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), B, H, W_, _stream()),
+          "dreamb200_first_conv3x3")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("first_conv3x3 %dx%d" % (H, W_), 2.0 * B * H * W_ * 64 * 27, e0, e1))
+    return y
+
+
 def im2col_first(x, R, S, stride, pad, Kpad):
     """fp32 NCHW [B,3,H,W] -> fp16 NHWC patches [B,Ho,Wo,Kpad] (k = (r*S+s)*3+c)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
@@ -203,8 +221,7 @@ def wgrad(dy, x, taps):
     B, H, W_, Co = dy.shape
     Ci = x.shape[3]
     assert tuple(x.shape[:3]) == (B, H, W_)
-    dy_cm = nhwc_to_cm(dy)
-    x_cm = nhwc_to_cm(x)
+    assert dy.dtype == torch.float16 and x.dtype == torch.float16 and dy.is_contiguous() and x.is_contiguous()
     dw = torch.zeros((len(taps), Co, Ci), dtype=torch.float32, device=dy.device)
     tdy = (C.c_int8 * len(taps))(*[t[0] for t in taps])
     tdx = (C.c_int8 * len(taps))(*[t[1] for t in taps])
@@ -212,7 +229,7 @@ def wgrad(dy, x, taps):
     if PROFILE is not None:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib().dreamb200_wgrad(_ptr(dy_cm), _ptr(x_cm), _ptr(dw), B, H, W_, dy_cm.shape[3], Co, Ci, len(taps),
+    check(lib().dreamb200_wgrad(_ptr(dy), _ptr(x), _ptr(dw), B, H, W_, Co, Ci, len(taps),
                                 C.cast(tdy, C.c_void_p), C.cast(tdx, C.c_void_p), _stream()), "dreamb200_wgrad")
     if PROFILE is not None:
         e1.record()

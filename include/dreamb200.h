@@ -65,6 +65,10 @@ int64_t dreamb200_launch_count(void);
 
 int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream);
 
+/* The network's first conv (3->64, 3x3 s1 p1, +bias +ReLU; models.py:591-599) fused with the input pack:
+   x fp32 NCHW [B,3,H,W], w fp16 [1][64][64] (k=(r*3+s)*3+c, zero padded), bias fp32 [64] -> y fp16 NHWC [B,H,W,64] */
+int dreamb200_first_conv3x3(const float* x, const void* w, const float* bias, void* y, int B, int H, int W,
+                            void* stream);
 /* x fp32 NCHW [B,3,H,W] -> out fp16 NHWC [B,Ho,Wo,Kpad]; k=(r*S+s)*3+c, zero padded */
 int dreamb200_im2col_first(const float* x, void* out, int B, int H, int W,
                            int R, int S, int stride, int pad, int Ho, int Wo, int Kpad, void* stream);
@@ -88,14 +92,12 @@ int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* g
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
 
 /* ---- backward (training) ------------------------------------------------------------------ */
-/* NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp % 8 == 0, pad columns zeroed): operand
-   layout of dreamb200_wgrad */
+/* NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp % 8 == 0, pad columns zeroed); utility */
 int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream);
-/* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy_cm/x_cm channel-major fp16 (above),
+/* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy, x NHWC fp16 [B,H,W,Cout_pad|Cin_pad],
    dw fp32 [taps][Cout_pad][Cin_pad] (caller zeroes it); autograd of nn.Conv2d weights */
-int dreamb200_wgrad(const void* dy_cm, const void* x_cm, float* dw, int B, int H, int W, int Wp,
-                    int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
-                    void* stream);
+int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
+                    int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream);
 /* dy *= (y > 0): autograd of nn.ReLU given its output */
 int dreamb200_relu_mask_f16(void* dy, const void* y, long long n, void* stream);
 /* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C] */

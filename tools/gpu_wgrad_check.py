@@ -10,9 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = []
-for bx in (64, 32, 16, 8):
-    for (B, H, W, Ci, Co) in [(2, 16, 24, 64, 64), (2, 16, 24, 64, 128), (3, 25, 25, 128, 256), (2, 50, 37, 256, 128)]:
-        CASES.append(("wgrad_bx%d_%dx%dx%d_%d_%d" % (bx, B, H, W, Ci, Co), bx, B, H, W, Ci, Co))
+for (B, H, W, Ci, Co) in [(1, 8, 16, 64, 64), (2, 16, 24, 64, 64), (2, 16, 24, 64, 128), (3, 25, 25, 128, 256),
+                          (2, 50, 37, 256, 128), (2, 13, 13, 512, 512)]:
+    CASES.append(("wgrad_%dx%dx%d_%d_%d" % (B, H, W, Ci, Co), 0, B, H, W, Ci, Co))
 CASES.append(("stream", 0, 0, 0, 0, 0, 0))
 CASES.append(("wgrad_auto_big_32x100x100_256_256", 0, 32, 100, 100, 256, 256))
 CASES.append(("wgrad_auto_big_8x400x400_64_64", 0, 8, 400, 400, 64, 64))
