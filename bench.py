@@ -30,6 +30,13 @@ GFLOP_PER_IMG = 141.7824          # vgg-Q @400x400 algorithmic conv FLOPs (SURVE
 B_PER_GPU = 128
 H = W = 400
 K_KP = 7
+# BASELINE.json configs; the default (headline) is configs[1].  name: (arch kwargs, batch/GPU, (H, W), GFLOP/img, mode)
+WORKLOADS = {
+    "vgg_q_infer": ({"type": "vgg"}, 128, (400, 400), 141.7824, "infer"),
+    "resnet_h_infer": ({"type": "resnet"}, 64, (400, 400), 82.870, "infer"),
+    "resnet_f_infer": ({"type": "resnet", "full_decoder": True}, 16, (480, 640), 315.546, "infer"),
+    "vgg_q_train": ({"type": "vgg"}, 128, (400, 400), 424.79, "train"),
+}
 
 
 def _peaks():
@@ -85,15 +92,18 @@ def _dist_env():
     return rank, world, local
 
 
-def make_config():
+def make_config(arch=None, res=(400, 400)):
     names = ["panda_link0", "panda_link2", "panda_link3", "panda_link4", "panda_link6", "panda_link7", "panda_hand"]
+    a = {"type": "vgg", "target": "belief_maps", "input_heads": ["image_rgb"], "output_heads": ["belief_maps"],
+         "image_normalization": {"mean": [0.5] * 3, "stdev": [0.5] * 3},
+         "loss": {"type": "mse"}, "image_preprocessing": "shrink-and-crop"}
+    a.update(arch or {})
     return {
-        "architecture": {"type": "vgg", "target": "belief_maps", "input_heads": ["image_rgb"],
-                         "output_heads": ["belief_maps"],
-                         "image_normalization": {"mean": [0.5] * 3, "stdev": [0.5] * 3},
-                         "loss": {"type": "mse"}, "image_preprocessing": "shrink-and-crop"},
+        "architecture": a,
         "manipulator": {"name": "panda", "keypoints": [{"name": n} for n in names]},
-        "training": {"config": {"net_input_resolution": [W, H]}, "platform": {"gpu_ids": []}},
+        "training": {"config": {"net_input_resolution": [res[1], res[0]],
+                                "optimizer": {"type": "adam", "learning_rate": 1.5e-4}},
+                     "platform": {"gpu_ids": []}},
     }
 
 
@@ -155,7 +165,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--workload", default="vgg_q_infer", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write per-layer timings (JSON) to this path")
     args = ap.parse_args()
@@ -176,23 +187,41 @@ def main():
     from dream_b200 import _lib, network, ops
     from dream_b200 import image_proc
 
-    B = args.batch
-    net = network.create_network_from_config_data(make_config())
-    net.enable_evaluation()
+    arch, b_default, (H, W), gflop_img, mode = WORKLOADS[args.workload]
+    B = args.batch or b_default
+    net = network.create_network_from_config_data(make_config(arch, (H, W)))
     model = net.model.module
+    if mode == "train":
+        net.enable_training()
+        from dream_b200 import distributed as D
+        D.broadcast_parameters(net.model)
+    else:
+        net.enable_evaluation()
     # synthetic inputs of the named shape; two batches (157 MB > L2) rotate, and every step streams
     # ~10 GB of activations, so nothing survives in the 126 MB L2 between timed iterations.
     g = torch.Generator(device=dev).manual_seed(rank)
     xs = [torch.rand((B, 3, H, W), device=dev, generator=g) * 2 - 1 for _ in range(2)]
     host_x = [x.cpu().pin_memory() for x in xs]
 
+    out_w, out_h = net.trained_net_output_resolution()
+    offset = 0.0 if (out_w >= 400 and out_h >= 400) else 0.4395
+    if mode == "train":
+        targets = [torch.rand((B, K_KP, out_h, out_w), device=dev, generator=g) for _ in range(2)]
+        host_t = [t.cpu().pin_memory() for t in targets]
+
     def step_device(i):
+        if mode == "train":          # fwd + MSE + bwd + gradient all-reduce + Adam step (DreamNetwork.train)
+            return net.train([xs[i & 1]], targets[i & 1])
         with torch.no_grad():
             belief = model.belief_maps(xs[i & 1])
-            table = image_proc.find_peaks_device(belief, 0.4395)
+            table = image_proc.find_peaks_device(belief, offset)
             return image_proc.select_keypoints_device(table, 0.25)
 
     def step_e2e(i):
+        if mode == "train":
+            x = host_x[i & 1].to(dev, non_blocking=True)
+            t = host_t[i & 1].to(dev, non_blocking=True)
+            return net.train([x], t).item()         # the loss read-back train_network.py:507 does every step
         with torch.no_grad():
             x = host_x[i & 1].to(dev, non_blocking=True)
             _, kps = net.inference(x)               # ends with the D2H copy of the keypoints
@@ -261,10 +290,10 @@ def main():
                 "launches_per_step": dn // reps, "kernel_ms_per_step": dt / reps,
                 "kernel_share_of_conv_time": dt / reps / total_ms,
                 "conv_stack": {"ms_per_step": total_ms,
-                               "algorithmic_tflops": GFLOP_PER_IMG * B / total_ms,
-                               "frac_of_peak": GFLOP_PER_IMG * B / total_ms / peak},
-                "whole_step": {"algorithmic_tflops": value / world * GFLOP_PER_IMG / 1e3,
-                               "frac_of_peak": value / world * GFLOP_PER_IMG / 1e3 / peak}}
+                               "algorithmic_tflops": gflop_img * B / total_ms,
+                               "frac_of_peak": gflop_img * B / total_ms / peak},
+                "whole_step": {"algorithmic_tflops": value / world * gflop_img / 1e3,
+                               "frac_of_peak": value / world * gflop_img / 1e3 / peak}}
         table = [{"layer": tag, "ms": t / reps, "tflops": f / t / 1e9, "launches": n // reps}
                  for tag, (t, f, n) in sorted(recs.items(), key=lambda kv: -kv[1][0])]
         if args.layer_table:
@@ -272,7 +301,7 @@ def main():
             json.dump({"batch": B, "layers": table, "roofline": roof}, open(args.layer_table, "w"), indent=1)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "vgg_q_infer":
         r, tf, tp, thr = cpu_baseline_sample(8)
         cpu = {"value": r, "unit": "images/s", "cores": thr, "kind": "port",
                "sample": "8 frames 400x400: oracle port of dream/models.py forward (%.2f s) + image_proc peaks (%.2f s)"
@@ -283,12 +312,17 @@ def main():
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
-            "config": {"workload": "DREAM-vgg-Q inference (forward + peak extraction), batch %d/GPU, 400x400, "
-                                   "7 keypoints" % B,
+            "config": {"workload": {"vgg_q_infer": "DREAM-vgg-Q inference (forward + peak extraction)",
+                                    "resnet_h_infer": "DREAM-resnet-H inference (forward + peak extraction)",
+                                    "resnet_f_infer": "DREAM-resnet-F inference (forward + peak extraction)",
+                                    "vgg_q_train": "DREAM-vgg-Q training step (fwd + MSE + bwd + allreduce + Adam)"}[
+                           args.workload] + ", batch %d/GPU, %dx%d, 7 keypoints" % (B, W, H),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "l2": "inputs rotate over 2 batches (157 MB > 126 MB L2); ~10 GB of activations stream per step"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
-                    "d2h_bytes_per_step": B * K_KP * 2 * 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "images/s",
+                    "h2d_bytes_per_step": B * 3 * H * W * 4 + (B * K_KP * out_h * out_w * 4 if mode == "train" else 0),
+                    "d2h_bytes_per_step": 4 if mode == "train" else B * K_KP * 2 * 4,
+                    "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
         ("out_mode", C.c_int32), ("cout_real", C.c_int32),
         ("residual", C.c_void_p),
         ("relu", C.c_int32),
-        ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p),
+        ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p), ("y_pool", C.c_void_p),
     ]
 
 
@@ -38,6 +38,7 @@ _PROTOS = {
     "dreamb200_last_error": (C.c_char_p, []),
     "dreamb200_version": (C.c_int, []),
     "dreamb200_launch_count": (C.c_int64, []),
+    "dreamb200_conv_tile_utilization": (C.c_double, [C.c_int] * 4),
     "dreamb200_conv2d_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "dreamb200_first_conv3x3": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "dreamb200_im2col_first": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
@@ -52,7 +53,8 @@ _PROTOS = {
     "dreamb200_nhwc_to_cm_f16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
                         [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "dreamb200_relu_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dreamb200_absmax_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_upsample2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_bias_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),

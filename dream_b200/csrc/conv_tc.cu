@@ -38,11 +38,14 @@ struct ConvParams {
   float* out_f32;
   int cout_real;
   int stages;
+  int pool;         // fused 2x2/s2 max pool of the output tile (tw, th even): pooled tile -> tmP
+  int store_full;   // also store the un-pooled tile through tmC
 };
 
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 fp16
 constexpr int kStageOutBytes = 128 * 128;
+constexpr int kPoolBytes = 32 * 128;    // pooled tile: <= 32 rows x 64 fp16
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -52,7 +55,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 template <int BLOCK_N, int OUT_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+               const __grid_constant__ ConvParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -66,7 +70,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = p.stages;
   const uint32_t smem_ab = smem_base;                                   // stages * kStageBytes
   const uint32_t smem_out = smem_ab + stages * kStageBytes;             // 2 * 16 KB (NHWC mode)
-  const uint32_t out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes : 0;
+  const uint32_t out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + 2 * kPoolBytes : 0;
+  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;             // 2 * 4 KB pooled staging
   const uint32_t bar_base = smem_out + out_bytes;                       // barriers (8 B each)
   // full[s], empty[s], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -83,7 +88,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (OUT_MODE == DREAMB200_OUT_NHWC_F16) tma_prefetch_desc(&tmC);
+    if (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
+      tma_prefetch_desc(&tmC);
+      if (p.pool) tma_prefetch_desc(&tmP);
+    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -193,7 +201,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
           const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
-          if (epi_tid == 0) tma_store_wait_read<1>();   // the store that used obuf has read it
+          const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
+          if (epi_tid == 0) {                            // stores that used obuf / pbuf two chunks ago have read them
+            if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+          }
           named_bar_sync(1, 128);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -262,9 +273,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (epi_tid == 0) {
+          if (epi_tid == 0 && (!p.pool || p.store_full)) {
             tma_store_4d(&tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
             tma_store_commit();
+          }
+          if (p.pool) {
+            // 2x2 max over the tile that now sits in obuf: pooled row pr, 16 B chunk ch per work item
+            const int ptw = p.tw >> 1;
+            const int items = ptw * (p.th >> 1) * 8;
+            for (int item = epi_tid; item < items; item += 128) {
+              const int pr = item >> 3, ch = item & 7;
+              const int py = pr / ptw, px = pr - py * ptw;
+              const int r00 = (2 * py) * p.tw + 2 * px;
+              __half2 m[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int r = r00 + (k >> 1) * p.tw + (k & 1);
+                uint32_t a0, a1, a2, a3;
+                const uint32_t src = obuf + (uint32_t)r * 128u + (((uint32_t)ch ^ (uint32_t)(r & 7)) * 16u);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src) : "memory");
+                const __half2 h0 = *reinterpret_cast<__half2*>(&a0), h1 = *reinterpret_cast<__half2*>(&a1);
+                const __half2 h2 = *reinterpret_cast<__half2*>(&a2), h3 = *reinterpret_cast<__half2*>(&a3);
+                if (k == 0) { m[0] = h0; m[1] = h1; m[2] = h2; m[3] = h3; }
+                else { m[0] = __hmax2(m[0], h0); m[1] = __hmax2(m[1], h1); m[2] = __hmax2(m[2], h2); m[3] = __hmax2(m[3], h3); }
+              }
+              const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)ch ^ (uint32_t)(pr & 7)) * 16u);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                           "r"(*reinterpret_cast<uint32_t*>(&m[0])), "r"(*reinterpret_cast<uint32_t*>(&m[1])),
+                           "r"(*reinterpret_cast<uint32_t*>(&m[2])), "r"(*reinterpret_cast<uint32_t*>(&m[3]))
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (epi_tid == 0) {
+              tma_store_4d(&tmP, pbuf, n * BLOCK_N + c * 64, tx * ptw, ty * (p.th >> 1), b);
+              tma_store_commit();
+            }
           }
         }
       } else {
@@ -337,14 +382,17 @@ int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint6
 
 // Pick the output patch (tw x th <= 128 pixels) that wastes the fewest accumulator rows.
 // `even` forces even patch sides (needed when a 2x2 pool is fused on top of the patch).
-static void choose_tile(int Wo, int Ho, int in_stride, int* tw_out, int* th_out) {
+static double choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, int* th_out) {
   double best = -1.0;
   int btw = 1, bth = 1;
   const int max_side = 256 / in_stride;  // TMA box side limit (in input elements)
-  for (int tw = 1; tw <= 128 && tw <= Wo && tw <= max_side; ++tw) {
+  const int step = even ? 2 : 1;
+  for (int tw = step; tw <= 128 && tw <= Wo + (even ? 1 : 0) && tw <= max_side; tw += step) {
     int th = 128 / tw;
-    if (th > Ho) th = Ho;
+    if (th > Ho + (even ? 1 : 0)) th = Ho + (even ? 1 : 0);
     if (th > max_side) th = max_side;
+    if (even) th &= ~1;
+    if (th < 1) continue;
     const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
     const double util = (double)Wo * Ho / (double)(tiles * 128);
     // on ties prefer the wider patch (longer contiguous runs per TMA row)
@@ -356,6 +404,7 @@ static void choose_tile(int Wo, int Ho, int in_stride, int* tw_out, int* th_out)
   }
   *tw_out = btw;
   *th_out = bth;
+  return best;
 }
 
 int device_sm_count();
@@ -364,7 +413,9 @@ template <int BLOCK_N, int OUT_MODE>
 static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  choose_tile(d->Wo, d->Ho, d->in_stride, &p.tw, &p.th);
+  choose_tile(d->Wo, d->Ho, d->in_stride, d->y_pool != nullptr, &p.tw, &p.th);
+  p.pool = d->y_pool != nullptr ? 1 : 0;
+  p.store_full = (d->y != nullptr) ? 1 : 0;
   p.tiles_x = (d->Wo + p.tw - 1) / p.tw;
   p.tiles_y = (d->Ho + p.th - 1) / p.th;
   p.n_tiles = d->Cout_pad / BLOCK_N;
@@ -387,7 +438,7 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   p.cout_real = d->cout_real;
 
   constexpr int kStageBytes = kABytes + BLOCK_N * 128;
-  const int out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes : 0;
+  const int out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + 2 * kPoolBytes : 0;
   const int budget = 232448 - 1024 - out_bytes - 512;
   int stages = budget / kStageBytes;
   if (stages > 8) stages = 8;
@@ -396,8 +447,9 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   const int smem_bytes = 1024 + stages * kStageBytes + out_bytes + 512;
 
   // A: activation NHWC (C, W, H, B); box (64, tw, th, 1); element stride = conv stride
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmP;
   memset(&tmC, 0, sizeof(tmC));
+  memset(&tmP, 0, sizeof(tmP));
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
@@ -414,7 +466,15 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
     uint32_t es[3] = {1, 1, 1};
     if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "weights")) return -1;
   }
-  if (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
+  if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && d->y_pool != nullptr) {
+    const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, Wp, Hp, (uint64_t)d->B};
+    uint64_t str[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw / 2, (uint32_t)p.th / 2, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es, "pooled output")) return -1;
+  }
+  if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && d->y != nullptr) {
     uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
     uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
@@ -429,7 +489,7 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
     attr_set = true;
   }
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, p);
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -450,15 +510,23 @@ int device_sm_count() {
 
 using namespace db200;
 
+extern "C" double dreamb200_conv_tile_utilization(int Wo, int Ho, int in_stride, int even) {
+  int tw, th;
+  return choose_tile(Wo, Ho, in_stride, even != 0, &tw, &th);
+}
+
 extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   DB_REQUIRE(d != nullptr, "conv: null descriptor");
-  DB_REQUIRE(d->x && d->w && d->y, "conv: null tensor pointer");
+  DB_REQUIRE(d->x && d->w && (d->y || d->y_pool), "conv: null tensor pointer");
+  DB_REQUIRE(d->y_pool == nullptr || (d->out_mode == DREAMB200_OUT_NHWC_F16 && d->Ho >= 2 && d->Wo >= 2),
+             "conv: fused pooling needs the NHWC_F16 mode and an output of at least 2x2");
   DB_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "conv: Cin=%d must be a positive multiple of 64", d->Cin);
   DB_REQUIRE(d->taps >= 1 && d->taps <= DREAMB200_MAX_TAPS, "conv: taps=%d out of range", d->taps);
   DB_REQUIRE(d->in_stride == 1 || d->in_stride == 2, "conv: stride %d unsupported", d->in_stride);
   DB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "conv: empty tensor");
-  DB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0,
+  DB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0 &&
+                 ((uintptr_t)d->y_pool & 15) == 0,
              "conv: tensors must be 16-byte aligned");
   const int sms = device_sm_count();
   if (d->out_mode == DREAMB200_OUT_NCHW_F32) {

@@ -217,18 +217,49 @@ __global__ void nhwc_to_cm_f16_kernel(const __half* __restrict__ x, __half* __re
   }
 }
 
-// dy *= (y > 0), fp16, 8 per thread
-__global__ void relu_mask_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, long long n8) {
+// dy = dy * scale * (y > 0): ReLU backward fused with the dynamic loss re-scaling; y and scale optional
+__global__ void scale_mask_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, const float* __restrict__ scale,
+                                  long long n8) {
   const __half2 zero = __float2half2_rn(0.0f);
+  const __half2 sc = __float2half2_rn(scale != nullptr ? __ldg(scale) : 1.0f);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
        idx += (long long)gridDim.x * blockDim.x) {
     uint4 g = dy[idx];
-    const uint4 a = __ldg(y + idx);
     __half2* gh = reinterpret_cast<__half2*>(&g);
-    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    if (y != nullptr) {
+      const uint4 a = __ldg(y + idx);
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) gh[j] = __hmul2(gh[j], __hgt2(ah[j], zero));
+      for (int j = 0; j < 4; ++j) gh[j] = __hmul2(__hmul2(gh[j], sc), __hgt2(ah[j], zero));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gh[j] = __hmul2(gh[j], sc);
+    }
     dy[idx] = g;
+  }
+}
+
+// out = max(out, max |x|) over an fp16 tensor; `out` holds the bits of a non-negative float (zeroed by the caller)
+__global__ void absmax_kernel(const uint4* __restrict__ x, long long n8, int* __restrict__ out) {
+  float m = 0.0f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(x + idx);
+    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(__habs2(vh[j]));
+      m = fmaxf(m, fmaxf(f.x, f.y));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sh[i]);
+    if (!(m <= 3.0e38f)) m = 3.0e38f;      // inf / nan -> huge, so the caller scales down
+    atomicMax(out, __float_as_int(m));
   }
 }
 
@@ -403,10 +434,19 @@ extern "C" int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, in
   return 0;
 }
 
-extern "C" int dreamb200_relu_mask_f16(void* dy, const void* y, long long n, void* stream) {
-  DB_REQUIRE(dy && y && n > 0 && n % 8 == 0, "relu_mask: bad arguments");
-  relu_mask_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<uint4*>(dy), reinterpret_cast<const uint4*>(y), n / 8);
+extern "C" int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream) {
+  DB_REQUIRE(dy && n > 0 && n % 8 == 0, "scale_mask: bad arguments");
+  scale_mask_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint4*>(dy), reinterpret_cast<const uint4*>(y), scale, n / 8);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream) {
+  DB_REQUIRE(x && out && n > 0 && n % 8 == 0, "absmax: bad arguments");
+  absmax_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), n / 8,
+                                                                       reinterpret_cast<int*>(out));
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -304,16 +304,29 @@ class DreamHourglass(_PlanModule):
         P = self.plan()
         t = ops.first_conv3x3(x, P["first"].w, P["first"].b)      # gather + pack + conv + bias + ReLU fused
         skips = {}
+        sk = self.skip_connections
+        pooled = None
         for bi, (block, idxs, _) in enumerate(VGG_TRUNK):
             if bi > 0:
-                t = ops.maxpool(t, 2, 2, 0)
+                t = pooled if pooled is not None else ops.maxpool(t, 2, 2, 0)
+                pooled = None
                 skips["pool%d" % bi] = t
             for j in idxs:
                 if block == "layer_0_1_down" and j == 0:
                     continue
-                t = _run_conv(P["%s.%d" % (block, j)], t)
+                pc = P["%s.%d" % (block, j)]
+                last = j == idxs[-1] and bi < len(VGG_TRUNK) - 1
+                if last and ops.pool_fusion_pays(t.shape[1], t.shape[2]):
+                    # nn.MaxPool2d(2) fused into this conv's epilogue; the un-pooled map is only kept
+                    # when a skip connection needs it (layer_0_1_down output, models.py:807)
+                    keep = sk and block == "layer_0_1_down"
+                    B, H, W, _c = t.shape
+                    full, pooled = ops.conv_taps(t, pc.w, pc.b, pc.taps, H, W, relu=pc.relu,
+                                                 pool="both" if keep else "only")
+                    t = full
+                else:
+                    t = _run_conv(pc, t)
             skips[block] = t
-        sk = self.skip_connections
         if sk:
             t = ops.add_(t.clone(), skips["pool4"])
         if self.deconv_decoder:

@@ -30,7 +30,7 @@ def round_up(v, m):
 
 
 def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
-              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None):
+              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None):
     """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
 
     x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
@@ -59,7 +59,13 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         d.out_mode = _lib.OUT_NCHW_F32; d.cout_real = head_cout
         d.y_stride_w = 1; d.y_stride_h = Wo; d.y_stride_b = head_cout * Ho * Wo
     else:
-        if y is None:
+        y_pool = None
+        if pool is not None:       # "only": pooled tensor only; "both": un-pooled tensor too (training tape)
+            y_pool = torch.empty((B, Ho // 2, Wo // 2, Cout_pad), dtype=torch.float16, device=x.device)
+            d.y_pool = y_pool.data_ptr()
+        if pool == "only":
+            y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
+        elif y is None:
             y = torch.empty((B, Ho, Wo, Cout_pad), dtype=torch.float16, device=x.device)
             y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
         elif y_strides is None:
@@ -67,7 +73,7 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
             y_strides = (Cout_pad, Wo * Cout_pad, Ho * Wo * Cout_pad)
         d.out_mode = _lib.OUT_NHWC_F16; d.cout_real = Cout_pad
         d.y_stride_w, d.y_stride_h, d.y_stride_b = y_strides
-    d.y = y.data_ptr() + y_offset * y.element_size()
+    d.y = (y.data_ptr() + y_offset * y.element_size()) if y is not None else None
     if residual is not None:
         assert residual.dtype == torch.float16 and residual.is_contiguous()
         assert tuple(residual.shape) == (B, Ho, Wo, Cout_pad)
@@ -84,9 +90,11 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         e1.record()
         block_n = 16 if head_cout is not None else (256 if Cout_pad % 256 == 0 else 128 if Cout_pad % 128 == 0 else 64)
         tag = "conv_tc<%d> T%d Cin%d Cout%d %dx%d s%d" % (block_n, T, Cin, Cout_pad, Ho, Wo, stride)
-        PROFILE.append((tag, 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
-        return y
-    check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
+        PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
+    else:
+        check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
+    if pool is not None and head_cout is None:
+        return (y, y_pool)
     return y
 
 
@@ -118,6 +126,13 @@ def im2col_first(x, R, S, stride, pad, Kpad):
     check(lib().dreamb200_im2col_first(_ptr(x), _ptr(out), B, H, W_, R, S, stride, pad, Ho, Wo, Kpad,
                                        _stream()), "dreamb200_im2col_first")
     return out
+
+
+def pool_fusion_pays(Ho, Wo, stride=1):
+    """Fusing the 2x2 pool into the conv epilogue forces even tile sides; worth it unless that wastes
+    noticeably more accumulator rows than the free tile choice (e.g. 50x50 maps)."""
+    l = lib()
+    return l.dreamb200_conv_tile_utilization(Wo, Ho, stride, 1) >= 0.9 * l.dreamb200_conv_tile_utilization(Wo, Ho, stride, 0)
 
 
 def maxpool(x, k, s, p):
@@ -238,10 +253,25 @@ def wgrad(dy, x, taps):
     return dw
 
 
-def relu_mask_(dy, y):
-    assert dy.shape == y.shape and dy.dtype == torch.float16 and y.dtype == torch.float16
-    check(lib().dreamb200_relu_mask_f16(_ptr(dy), _ptr(y), dy.numel(), _stream()), "dreamb200_relu_mask_f16")
+def scale_mask_(dy, y=None, scale=None):
+    """dy = dy * scale * (y > 0) in place; y (fp16, same shape) and scale (1-element fp32 cuda tensor) optional."""
+    assert dy.dtype == torch.float16 and dy.is_contiguous()
+    if y is not None:
+        assert y.shape == dy.shape and y.dtype == torch.float16 and y.is_contiguous()
+    check(lib().dreamb200_scale_mask_f16(_ptr(dy), _ptr(y), _ptr(scale), dy.numel(), _stream()),
+          "dreamb200_scale_mask_f16")
     return dy
+
+
+def relu_mask_(dy, y):
+    return scale_mask_(dy, y)
+
+
+def absmax(x):
+    """max |x| of an fp16 tensor as a 1-element fp32 cuda tensor (no host sync)."""
+    out = torch.zeros((1,), dtype=torch.float32, device=x.device)
+    check(lib().dreamb200_absmax_f16(_ptr(x), x.numel(), _ptr(out), _stream()), "dreamb200_absmax_f16")
+    return out
 
 
 def maxpool2_bwd(x, dy):

@@ -56,7 +56,14 @@ typedef struct dreamb200_conv_desc {
      of the (post-ReLU) output next to the fp16 one. Both [B,Ho,Wo,Cout_pad] or NULL. */
   const float* residual_f32;
   float* y_f32;
+  /* fused nn.MaxPool2d(2) (models.py:589): when set, the 2x2/s2 (floor) max pool of the output is written
+     here, fp16 NHWC dense [B,Ho/2,Wo/2,Cout_pad]; `y` may then be NULL (un-pooled tensor not stored). */
+  void* y_pool;
 } dreamb200_conv_desc;
+
+/* fraction of the 128 accumulator rows a conv with this output size keeps busy, for the free tile
+   choice (even=0) or with even tile sides as fused pooling needs (even=1); lets callers decide on fusion */
+double dreamb200_conv_tile_utilization(int Wo, int Ho, int in_stride, int even);
 
 const char* dreamb200_last_error(void);
 int dreamb200_version(void);
@@ -98,8 +105,11 @@ int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C,
    dw fp32 [taps][Cout_pad][Cin_pad] (caller zeroes it); autograd of nn.Conv2d weights */
 int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
                     int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream);
-/* dy *= (y > 0): autograd of nn.ReLU given its output */
-int dreamb200_relu_mask_f16(void* dy, const void* y, long long n, void* stream);
+/* dy = dy * (*scale) * (y > 0): autograd of nn.ReLU given its output, fused with the power-of-two
+   re-scaling that keeps fp16 gradients in range; y and/or scale may be NULL */
+int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream);
+/* *out = max(*out, max|x|) over n fp16 values (out: device float, zeroed by the caller) */
+int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream);
 /* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C] */
 int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 /* autograd of nn.Upsample(scale_factor=2): dy [B,2H,2W,C] -> dx [B,H,W,C] */

@@ -154,6 +154,44 @@ def test_single_layers_are_exact_up_to_output_rounding(B, H, W, Cin, Cout, ksz, 
         assert float(y[..., Cout:].abs().max()) == 0.0          # padded channels stay exactly zero
 
 
+@pytest.mark.parametrize("B,H,W,C,Co", [(2, 32, 48, 64, 64), (2, 50, 50, 128, 128), (1, 37, 53, 64, 128),
+                                         (2, 100, 100, 256, 256), (3, 200, 200, 64, 64)])
+def test_fused_pool_equals_conv_then_pool(B, H, W, C, Co, built_lib):
+    """The 2x2 max pool fused into the conv epilogue is bit-identical to conv followed by the pool kernel."""
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn((B, H, W, C), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((Co, C, 3, 3), device="cuda", generator=g) * (1.0 / (C * 9) ** 0.5)
+    b = torch.randn((Co,), device="cuda", generator=g) * 0.1
+    rs = [(r, s) for r in range(3) for s in range(3)]
+    wp, bp = ops.pack_conv_weight(w, rs), ops.pad_bias(b, ops.round_up(Co, 64), "cuda")
+    y = ops.conv_taps(x, wp, bp, ops.TAPS_3x3, H, W, relu=True)
+    ref_pool = ops.maxpool(y, 2, 2, 0)
+    full, pooled = ops.conv_taps(x, wp, bp, ops.TAPS_3x3, H, W, relu=True, pool="both")
+    assert torch.equal(full, y) and torch.equal(pooled, ref_pool)
+    none, pooled2 = ops.conv_taps(x, wp, bp, ops.TAPS_3x3, H, W, relu=True, pool="only")
+    assert none is None and torch.equal(pooled2, ref_pool)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 80), (1, 37, 53), (3, 400, 400)])
+def test_fused_first_conv_matches_patch_path_and_torch(B, H, W, built_lib):
+    """first_conv3x3 (gather + pack + MMA fused) vs the im2col + 1-tap GEMM path (same fp16 operands) and fp32."""
+    import torch.nn.functional as F
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.rand((B, 3, H, W), device="cuda", generator=g) * 2 - 1
+    w = torch.randn((64, 3, 3, 3), device="cuda", generator=g) * 0.2
+    b = torch.randn((64,), device="cuda", generator=g) * 0.1
+    wp, bp = ops.pack_first_weight(w, 64), ops.pad_bias(b, 64, "cuda")
+    y = ops.first_conv3x3(x, wp, bp)
+    y2 = ops.conv_taps(ops.im2col_first(x, 3, 3, 1, 1, 64), wp, bp, [(0, 0)], H, W, relu=True)
+    ref = F.relu(F.conv2d(x.half().double(), w.half().double(), b.double(), padding=1)).float()
+    got = y.permute(0, 3, 1, 2).float()
+    tol = ref.abs() * 2.0 ** -11 + 1e-5 * ref.abs().max()
+    assert bool(((got - ref).abs() <= tol).all())
+    assert (y.float() - y2.float()).abs().max().item() <= 2.0 ** -10 * ref.abs().max().item()
+
+
 def test_state_dict_round_trip_with_module_prefix(built_lib):
     from dream_b200 import models
     sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=2)

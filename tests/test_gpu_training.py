@@ -112,7 +112,7 @@ def test_training_steps_track_oracle_loss_curve(built_lib):
     from dream_b200 import network
     cfg = panda_config("vgg")
     cfg["training"]["config"]["net_input_resolution"] = [96, 64]
-    cfg["training"]["config"]["optimizer"] = {"type": "sgd", "learning_rate": 0.05}
+    cfg["training"]["config"]["optimizer"] = {"type": "sgd", "learning_rate": 0.002}
     net = network.create_network_from_config_data(cfg)
     sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=5, out_gain=0.1, mode="he")
     net.model.load_state_dict(sd)
@@ -121,7 +121,7 @@ def test_training_steps_track_oracle_loss_curve(built_lib):
     x = torch.rand((4, 3, 64, 96), generator=gen) * 2 - 1
     t = torch.rand((4, 7, 16, 24), generator=gen)
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.SGD(list(osd.values()), lr=0.05)
+    opt = torch.optim.SGD(list(osd.values()), lr=0.002)
     for step in range(4):
         loss = net.train([x.cuda()], t.cuda())
         opt.zero_grad()

@@ -151,7 +151,7 @@ def main():
         t0 = time.time()
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", c[0]],
-                               capture_output=True, text=True, timeout=120)
+                               capture_output=True, text=True, timeout=45)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             r = json.loads(line[-1][7:]) if line else {"name": c[0], "ok": False, "error": "no result",
                                                         "stderr": p.stderr[-800:], "stdout": p.stdout[-800:]}

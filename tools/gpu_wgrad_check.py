@@ -48,6 +48,9 @@ def run_case(name):
         ref_mask = d.float() * (y.float() > 0)
         got = ops.relu_mask_(d.clone(), y)
         e3 = (got.float() - ref_mask).abs().max().item()
+        sc = torch.full((1,), 4.0, device="cuda")
+        e3 += (ops.scale_mask_(d.clone(), y, sc).float() - 4 * ref_mask).abs().max().item()
+        e3 += abs(ops.absmax(d).item() - d.float().abs().max().item())
         db = ops.bias_grad(got)
         e4 = (db - ref_mask.sum(dim=(0, 1, 2))).abs().max().item()
         cm = ops.nhwc_to_cm(x)
@@ -95,7 +98,7 @@ def main():
         t0 = time.time()
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", c[0]],
-                               capture_output=True, text=True, timeout=120)
+                               capture_output=True, text=True, timeout=45)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             r = json.loads(line[-1][7:]) if line else {"name": c[0], "ok": False, "error": "no result",
                                                         "stderr": p.stderr[-400:], "stdout": p.stdout[-400:]}
