@@ -19,6 +19,11 @@ import torch
 
 from . import models, ops
 
+# Test hook: when set to a list, backward appends one record per conv layer:
+# (key, dY as fed to the layer's kernels [fp16, already scaled+masked], cumulative scale [1-elem tensor],
+#  layer input [fp16 NHWC], dX produced [fp16 NHWC or None]).  None = no capture, no cost.
+DEBUG_CAPTURE = None
+
 
 def _dgrad_pack(weight, cin_pad, cout_pad):
     """Weights for the data gradient of a 3x3 'same' conv: dX[q] = sum_rs dY[q-(r-1,s-1)] W[:,:,r,s]^T."""
@@ -105,7 +110,12 @@ class _HourglassTrainFn(torch.autograd.Function):
                     grads[key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
                     B, H, W, _ = xin.shape
+                    g_in = g
                     g = ops.conv_taps(g, wd, None, taps, H, W)
+                    if DEBUG_CAPTURE is not None:
+                        DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g))
+                if kind == "first" and DEBUG_CAPTURE is not None:
+                    DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None))
             elif kind == "pool":
                 g = ops.maxpool2_bwd(xin, g)
             elif kind == "up":

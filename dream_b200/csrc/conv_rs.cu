@@ -1,0 +1,313 @@
+// conv_rs.cu -- "row-shared" variant of the 3x3 / stride 1 / pad 1 tensor-core convolution for the layers that are
+// L2->SMEM bandwidth bound in conv_tc.cu (few output channels: every MMA k-block there re-fetches a 16 KB
+// activation tile for only 64 or 128 output channels).
+//
+// Output tile = 8 (x) x 16 (y) pixels.  For one 64-channel chunk the producer loads three activation slabs, one
+// per horizontal tap s: a TMA box (64 ch, 8 x, 18 y) at x0-1+s, y0-1.  8 pixels x 128 B is exactly one 1024-byte
+// SWIZZLE_128B row group, so inside a slab image row yy is row group yy, and the A operand of the vertical tap r
+// is the SAME slab read from byte offset r*1024 -- a 1024-aligned start address, i.e. a perfectly ordinary UMMA
+// descriptor.  Three taps share one load: activation traffic per tile and chunk drops from 9 x 16 KB to 3 x 18 KB.
+// When all 9 x Cin/64 weight tiles fit (64 -> 64 channels: 72 KB) they are loaded once per CTA and stay resident,
+// otherwise they stream through their own ring.  Epilogue, pooling fusion and parameter block are conv_tc's.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "dreamb200.h"
+
+#include <stdlib.h>
+
+namespace db200 {
+
+int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride,
+                        const char* what);
+int device_sm_count();
+
+constexpr int kRsTw = 8, kRsTh = 16;
+constexpr int kSlabBytes = 18 * 1024;   // 18 image rows x 8 pixels x 128 B
+
+struct RsExtra {
+  int sa, sb;        // ring depths: activation slabs, weight tiles
+};
+
+template <int BLOCK_N, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+               const __grid_constant__ ConvParams p, const __grid_constant__ RsExtra x) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : 256;
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int sa = x.sa, sb = x.sb;
+  const int n_wtiles = 9 * p.kchunks;                                   // resident weight tiles
+  const uint32_t smem_a = smem_base;                                    // sa slabs
+  const uint32_t smem_b = smem_a + sa * kSlabBytes;                     // sb tiles (ring) or n_wtiles tiles (resident)
+  const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : sb) * kBBytes;
+  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
+  const uint32_t bar_base = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (sa + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * sa + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * sa + sb + s); };
+  const uint32_t misc = bar_base + 8u * (2 * sa + 2 * sb);
+  auto tfull_bar = [&](int a) { return misc + 8u * a; };
+  auto tempty_bar = [&](int a) { return misc + 16u + 8u * a; };
+  const uint32_t wbar = misc + 32u;
+  const uint32_t tmem_ptr_smem = misc + 40u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.pool) tma_prefetch_desc(&tmP);
+    for (int s = 0; s < sa; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (RESIDENT) {   // this CTA's n is fixed (n_tiles == 1 for resident layers): all weight tiles once
+        mbar_expect_tx(wbar, (uint32_t)(n_wtiles * kBBytes));
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_3d(smem_b + (tap * p.kchunks + kc) * kBBytes, &tmB, wbar, kc * 64, 0, tap);
+      }
+      int as_ = 0, bs_ = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n = tile % p.n_tiles;
+        int t = tile / p.n_tiles;
+        int tx = t % p.tiles_x; t /= p.tiles_x;
+        int ty = t % p.tiles_y;
+        int b = t / p.tiles_y;
+        const int x0 = tx * kRsTw, y0 = ty * kRsTh;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(aempty(as_), aph ^ 1u);
+            mbar_expect_tx(afull(as_), (uint32_t)kSlabBytes);
+            tma_load_4d(smem_a + as_ * kSlabBytes, &tmA, afull(as_), kc * 64, x0 - 1 + s, y0 - 1, b);
+            if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+            if (!RESIDENT) {
+              for (int r = 0; r < 3; ++r) {
+                mbar_wait(bempty(bs_), bph ^ 1u);
+                mbar_expect_tx(bfull(bs_), (uint32_t)kBBytes);
+                tma_load_3d(smem_b + bs_ * kBBytes, &tmB, bfull(bs_), kc * 64, n * BLOCK_N, r * 3 + s);
+                if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      if (RESIDENT) mbar_wait(wbar, 0);
+      int as_ = 0, bs_ = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t accph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), accph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        uint32_t first = 1u;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(afull(as_), aph);
+            tc_fence_after();
+            const uint32_t slab = smem_a + as_ * kSlabBytes;
+            for (int r = 0; r < 3; ++r) {
+              uint32_t btile;
+              if (RESIDENT) {
+                btile = smem_b + ((r * 3 + s) * p.kchunks + kc) * kBBytes;
+              } else {
+                mbar_wait(bfull(bs_), bph);
+                tc_fence_after();
+                btile = smem_b + bs_ * kBBytes;
+              }
+              const uint64_t adesc = umma_desc_k_sw128(slab + r * 1024);   // vertical tap = row-group offset
+              const uint64_t bdesc = umma_desc_k_sw128(btile);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, first ? 0u : 1u);
+                first = 0u;
+              }
+              if (!RESIDENT) {
+                umma_commit(bempty(bs_));
+                if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
+              }
+            }
+            umma_commit(aempty(as_));
+            if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) accph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    const int ly = row / kRsTw, lx = row - ly * kRsTw;
+    int acc = 0;
+    uint32_t accph = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      int tx = t % p.tiles_x; t /= p.tiles_x;
+      int ty = t % p.tiles_y;
+      int b = t / p.tiles_y;
+      const int ox = tx * kRsTw + lx, oy = ty * kRsTh + ly;
+      const bool valid = (ox < p.Wo) && (oy < p.Ho);
+      mbar_wait(tfull_bar(acc), accph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, tempty_bar(acc), n, tx, ty, b, ox, oy,
+                                  valid, row, lane, epi_tid, chunk_ctr);
+      acc ^= 1;
+      if (acc == 0) accph ^= 1u;
+    }
+    if (epi_tid == 0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, bool RESIDENT>
+static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = kRsTw; p.th = kRsTh;
+  p.tiles_x = (d->Wo + kRsTw - 1) / kRsTw;
+  p.tiles_y = (d->Ho + kRsTh - 1) / kRsTh;
+  p.n_tiles = d->Cout_pad / BLOCK_N;
+  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * d->B;
+  p.in_stride = 1;
+  p.taps = 9;
+  p.kchunks = d->Cin / 64;
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.residual_f32 = d->residual_f32;
+  p.y_f32 = d->y_f32;
+  p.Cout_pad = d->Cout_pad;
+  p.relu = d->relu;
+  p.pool = d->y_pool != nullptr ? 1 : 0;
+  p.store_full = d->y != nullptr ? 1 : 0;
+
+  constexpr int kBBytes = BLOCK_N * 128;
+  const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
+  RsExtra x;
+  int budget = 232448 - 1024 - out_bytes - 1024;
+  if (RESIDENT) {
+    budget -= 9 * p.kchunks * kBBytes;
+    x.sa = budget / kSlabBytes;
+    if (x.sa > 8) x.sa = 8;
+    x.sb = 1;
+  } else {
+    x.sa = 4;
+    x.sb = (budget - x.sa * kSlabBytes) / kBBytes;
+    if (x.sb > 12) x.sb = 12;
+  }
+  DB_REQUIRE(x.sa >= 3 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs: shared memory budget too small");
+  const int smem_bytes = 1024 + x.sa * kSlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBBytes + out_bytes + 1024;
+
+  CUtensorMap tmA, tmB, tmC, tmP;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmP, 0, sizeof(tmP));
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+    uint32_t box[4] = {64, kRsTw, kRsTh + 2, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es, "rs activation")) return -1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, 9};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {64, (uint32_t)BLOCK_N, 1};
+    uint32_t es[3] = {1, 1, 1};
+    if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "rs weights")) return -1;
+  }
+  if (d->y_pool != nullptr) {
+    const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, Wp, Hp, (uint64_t)d->B};
+    uint64_t str[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+    uint32_t box[4] = {64, kRsTw / 2, kRsTh / 2, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es, "rs pooled output")) return -1;
+  }
+  if (d->y != nullptr) {
+    uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
+    uint32_t box[4] = {64, kRsTw, kRsTh, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "rs output")) return -1;
+  }
+  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p, x);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Returns 1 and launches when the layer qualifies for the row-shared kernel, 0 when conv_tc should handle it,
+// <0 on error.
+int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  static double min_util = -1.0;
+  if (min_util < 0.0) {
+    const char* e = getenv("DREAMB200_RS_MIN_UTIL");   // 2.0 disables the kernel (A/B measurements)
+    min_util = e ? atof(e) : 0.85;
+  }
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->taps != 9 || d->in_stride != 1) return 0;
+  if (d->Ho != d->H || d->Wo != d->W) return 0;
+  if (d->Cout_pad % 256 == 0) return 0;                 // wide layers are tensor-bound already in conv_tc
+  for (int t = 0; t < 9; ++t)
+    if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1) return 0;
+  const double util = (double)d->Wo * d->Ho /
+                      ((double)((d->Wo + kRsTw - 1) / kRsTw) * ((d->Ho + kRsTh - 1) / kRsTh) * 128.0);
+  if (util < min_util) return 0;
+  int rc;
+  if (d->Cout_pad % 128 == 0) {
+    rc = launch_rs<128, false>(d, stream);
+  } else if (d->Cout_pad == 64 && d->Cin == 64) {
+    rc = launch_rs<64, true>(d, stream);
+  } else {
+    rc = launch_rs<64, false>(d, stream);
+  }
+  return rc == 0 ? 1 : rc;
+}
+
+}  // namespace db200

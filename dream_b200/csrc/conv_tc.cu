@@ -16,41 +16,12 @@
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = MMA issuer + TMEM owner, warps2-5 = epilogue.
 // Persistent: grid = #SMs, tiles round-robin.
 #include "common.cuh"
+#include "conv_common.cuh"
 #include "dreamb200.h"
 
 #include <mutex>
 
 namespace db200 {
-
-struct ConvParams {
-  int tiles_x, tiles_y, n_tiles, total_tiles;
-  int tw, th;
-  int B, Ho, Wo;
-  int in_stride;
-  int taps, kchunks;
-  int8_t dy[DREAMB200_MAX_TAPS], dx[DREAMB200_MAX_TAPS];
-  const float* bias;
-  const __half* residual;
-  const float* residual_f32;   // fp32 NHWC residual stream (ResNet identity path), or NULL
-  float* y_f32;                // optional fp32 NHWC copy of the output (next block's identity)
-  int Cout_pad;
-  int relu;
-  float* out_f32;
-  int cout_real;
-  int stages;
-  int pool;         // fused 2x2/s2 max pool of the output tile (tw, th even): pooled tile -> tmP
-  int store_full;   // also store the un-pooled tile through tmC
-};
-
-constexpr int kThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 rows x 64 fp16
-constexpr int kStageOutBytes = 128 * 128;
-constexpr int kPoolBytes = 32 * 128;    // pooled tile: <= 32 rows x 64 fp16
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 template <int BLOCK_N, int OUT_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -70,8 +41,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = p.stages;
   const uint32_t smem_ab = smem_base;                                   // stages * kStageBytes
   const uint32_t smem_out = smem_ab + stages * kStageBytes;             // 2 * 16 KB (NHWC mode)
-  const uint32_t out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + 2 * kPoolBytes : 0;
-  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;             // 2 * 4 KB pooled staging
+  const uint32_t out_bytes =
+      (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0) : 0;
+  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;             // 2 * 4 KB pooled staging (pool only)
   const uint32_t bar_base = smem_out + out_bytes;                       // barriers (8 B each)
   // full[s], empty[s], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -191,127 +163,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
-        const __half* res_row = nullptr;
-        const float* res32_row = nullptr;
-        float* y32_row = nullptr;
-        const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
-        if (p.residual != nullptr && valid) res_row = p.residual + row_off;
-        if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
-        if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
-          const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
-          const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
-          if (epi_tid == 0) {                            // stores that used obuf / pbuf two chunks ago have read them
-            if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
-          }
-          named_bar_sync(1, 128);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
-            tmem_wait_ld();
-            const int ch0 = n * BLOCK_N + c * 64 + h * 32;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
-                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-              }
-            }
-            if (res_row != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64 + h * 32 + i));
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 rf = __half22float2(rh[j]);
-                  f[i + 2 * j] += rf.x;
-                  f[i + 2 * j + 1] += rf.y;
-                }
-              }
-            }
-            if (res32_row != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
-                f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            if (y32_row != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) =
-                    make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w0 = pack_h2(f[8 * j + 0], f[8 * j + 1]);
-              const uint32_t w1 = pack_h2(f[8 * j + 2], f[8 * j + 3]);
-              const uint32_t w2 = pack_h2(f[8 * j + 4], f[8 * j + 5]);
-              const uint32_t w3 = pack_h2(f[8 * j + 6], f[8 * j + 7]);
-              const uint32_t chunk16 = (uint32_t)(h * 4 + j) ^ (uint32_t)(row & 7);
-              const uint32_t dst = obuf + (uint32_t)row * 128u + chunk16 * 16u;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1),
-                           "r"(w2), "r"(w3)
-                           : "memory");
-            }
-          }
-          if (c == BLOCK_N / 64 - 1) {
-            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (epi_tid == 0 && (!p.pool || p.store_full)) {
-            tma_store_4d(&tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
-            tma_store_commit();
-          }
-          if (p.pool) {
-            // 2x2 max over the tile that now sits in obuf: pooled row pr, 16 B chunk ch per work item
-            const int ptw = p.tw >> 1;
-            const int items = ptw * (p.th >> 1) * 8;
-            for (int item = epi_tid; item < items; item += 128) {
-              const int pr = item >> 3, ch = item & 7;
-              const int py = pr / ptw, px = pr - py * ptw;
-              const int r00 = (2 * py) * p.tw + 2 * px;
-              __half2 m[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int r = r00 + (k >> 1) * p.tw + (k & 1);
-                uint32_t a0, a1, a2, a3;
-                const uint32_t src = obuf + (uint32_t)r * 128u + (((uint32_t)ch ^ (uint32_t)(r & 7)) * 16u);
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src) : "memory");
-                const __half2 h0 = *reinterpret_cast<__half2*>(&a0), h1 = *reinterpret_cast<__half2*>(&a1);
-                const __half2 h2 = *reinterpret_cast<__half2*>(&a2), h3 = *reinterpret_cast<__half2*>(&a3);
-                if (k == 0) { m[0] = h0; m[1] = h1; m[2] = h2; m[3] = h3; }
-                else { m[0] = __hmax2(m[0], h0); m[1] = __hmax2(m[1], h1); m[2] = __hmax2(m[2], h2); m[3] = __hmax2(m[3], h3); }
-              }
-              const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)ch ^ (uint32_t)(pr & 7)) * 16u);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                           "r"(*reinterpret_cast<uint32_t*>(&m[0])), "r"(*reinterpret_cast<uint32_t*>(&m[1])),
-                           "r"(*reinterpret_cast<uint32_t*>(&m[2])), "r"(*reinterpret_cast<uint32_t*>(&m[3]))
-                           : "memory");
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (epi_tid == 0) {
-              tma_store_4d(&tmP, pbuf, n * BLOCK_N + c * 64, tx * ptw, ty * (p.th >> 1), b);
-              tma_store_commit();
-            }
-          }
-        }
+        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, tempty_bar(as), n, tx, ty, b, ox, oy,
+                                    valid, row, lane, epi_tid, chunk_ctr);
       } else {
         // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
         uint32_t v[16];
@@ -408,6 +261,7 @@ static double choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out,
 }
 
 int device_sm_count();
+int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream);   // conv_rs.cu
 
 template <int BLOCK_N, int OUT_MODE>
 static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
@@ -438,7 +292,8 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   p.cout_real = d->cout_real;
 
   constexpr int kStageBytes = kABytes + BLOCK_N * 128;
-  const int out_bytes = (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + 2 * kPoolBytes : 0;
+  const int out_bytes =
+      (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0) : 0;
   const int budget = 232448 - 1024 - out_bytes - 512;
   int stages = budget / kStageBytes;
   if (stages > 8) stages = 8;
@@ -541,6 +396,10 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
              d->Cout_pad);
   DB_REQUIRE((d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0,
              "conv: output strides must be multiples of 16 bytes");
+  {
+    const int r = try_conv_rs(d, stream);      // row-shared kernel for the narrow 3x3 layers
+    if (r != 0) return r > 0 ? 0 : r;
+  }
   if (d->Cout_pad % 256 == 0) return launch<256, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
   if (d->Cout_pad % 128 == 0) return launch<128, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
   return launch<64, DREAMB200_OUT_NHWC_F16>(d, stream, sms);

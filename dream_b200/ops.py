@@ -4,6 +4,7 @@ Tensors are only carriers of device memory here: every op hands raw pointers and
 current CUDA stream to libdreamb200.so.  Activations are NHWC fp16 (`[B,H,W,C]`, C % 64 == 0).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -89,7 +90,9 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
         e1.record()
         block_n = 16 if head_cout is not None else (256 if Cout_pad % 256 == 0 else 128 if Cout_pad % 128 == 0 else 64)
-        tag = "conv_tc<%d> T%d Cin%d Cout%d %dx%d s%d" % (block_n, T, Cin, Cout_pad, Ho, Wo, stride)
+        rs = (T == 9 and stride == 1 and block_n in (64, 128) and tuple(taps) == tuple(TAPS_3x3) and
+              Ho * Wo / (((Wo + 7) // 8) * ((Ho + 15) // 16) * 128.0) >= float(os.environ.get("DREAMB200_RS_MIN_UTIL", 0.85)))
+        tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % ("conv_rs" if rs else "conv_tc", block_n, T, Cin, Cout_pad, Ho, Wo, stride)
         PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
     else:
         check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")

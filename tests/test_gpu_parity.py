@@ -119,7 +119,10 @@ def test_network_forward_matches_oracle_fullres(name, shape, mode, built_lib):
     (2, 32, 32, 64, 64, 3, 1, ""), (2, 40, 40, 64, 128, 3, 1, ""), (2, 25, 25, 128, 256, 3, 1, ""),
     (2, 50, 50, 256, 512, 3, 1, ""), (4, 25, 25, 512, 512, 3, 1, ""), (2, 100, 100, 64, 64, 3, 1, "res"),
     (2, 100, 100, 64, 7, 3, 1, "head"), (2, 50, 50, 256, 64, 1, 1, ""), (2, 50, 50, 128, 128, 3, 2, ""),
-    (2, 25, 25, 256, 512, 1, 2, ""), (1, 13, 13, 2048, 256, 1, 1, "")])
+    (2, 25, 25, 256, 512, 1, 2, ""), (1, 13, 13, 2048, 256, 1, 1, ""),
+    # row-shared kernel (conv_rs.cu): streamed weights N=128 / N=64, resident weights, partial tiles
+    (2, 64, 64, 64, 128, 3, 1, ""), (2, 48, 64, 128, 128, 3, 1, ""), (2, 32, 32, 128, 64, 3, 1, ""),
+    (1, 30, 45, 64, 64, 3, 1, ""), (2, 200, 200, 128, 128, 3, 1, "")])
 def test_single_layers_are_exact_up_to_output_rounding(B, H, W, Cin, Cout, ksz, stride, extra, built_lib):
     """One conv layer on identical fp16 operands vs an fp32 conv: error <= one fp16 ulp of the output
     (the store rounding) + fp32 accumulation noise; the fp32 head output must agree to 1e-5 relative."""
@@ -155,7 +158,8 @@ def test_single_layers_are_exact_up_to_output_rounding(B, H, W, Cin, Cout, ksz, 
 
 
 @pytest.mark.parametrize("B,H,W,C,Co", [(2, 32, 48, 64, 64), (2, 50, 50, 128, 128), (1, 37, 53, 64, 128),
-                                         (2, 100, 100, 256, 256), (3, 200, 200, 64, 64)])
+                                         (2, 100, 100, 256, 256), (3, 200, 200, 64, 64), (2, 64, 64, 128, 128),
+                                         (1, 31, 46, 64, 64)])
 def test_fused_pool_equals_conv_then_pool(B, H, W, C, Co, built_lib):
     """The 2x2 max pool fused into the conv epilogue is bit-identical to conv followed by the pool kernel."""
     from dream_b200 import ops

@@ -74,8 +74,21 @@ def test_streaming_backward_kernels_match_torch(built_lib):
     assert (db - ref_mask.sum(dim=(0, 1, 2))).abs().max() <= 1e-3 * ref_mask.abs().sum(dim=(0, 1, 2)).max()
 
 
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
 @pytest.mark.parametrize("fixture", ["vgg_q", "vgg_q_he"])
 def test_hourglass_gradients_match_oracle_and_golden(fixture, golden_dir, built_lib):
+    """End-to-end gradients vs the oracle's fp32 autograd (and the reference's golden gradients).
+
+    The loss and the last layers' gradients must agree to 1e-3 / 1e-2.  Deeper into the backward pass an fp16
+    forward cannot reproduce an fp32 one bit for bit: ~0.1 % of ReLU / max-pool decisions per layer fall on
+    the other side (|pre-activation| below the 1e-3 forward noise), and each flipped unit changes its whole
+    gradient path, so the max-abs error grows like sqrt(flipped fraction) per layer (measured: 1e-4 at the
+    head, 1-4 % in the trunk, ~10 % at the first conv, cosine >= 0.99 throughout).  That part is therefore
+    gated on direction and norm; exactness of every backward kernel given identical inputs is
+    test_backward_kernels_layerwise_teacher_forced."""
     from dream_b200 import models
     g = np.load(os.path.join(golden_dir, "net_%s.npz" % fixture))
     shapes = ref_models.vgg_state_shapes(7, prefix="")
@@ -95,15 +108,61 @@ def test_hourglass_gradients_match_oracle_and_golden(fixture, golden_dir, built_
     worst = 0.0
     for name, p in net.named_parameters():
         assert p.grad is not None, name
-        r = _rel(p.grad.cpu(), ref_grads[name])
+        got, ref = p.grad.cpu(), ref_grads[name]
+        r = _rel(got, ref)
         worst = max(worst, r)
-        assert r <= 1e-2, (name, r)
-    print("worst per-parameter grad rel err:", worst)
+        if name.startswith("heads_0") or name.startswith("upsample_0_3"):
+            assert r <= 1e-2, (name, r)
+        assert _cos(got, ref) >= 0.985, (name, _cos(got, ref))
+        assert abs(float(got.norm() / ref.norm()) - 1.0) <= 0.03, (name, float(got.norm() / ref.norm()))
+    print("worst per-parameter max-abs rel err:", worst)
     for key in g.files:
         if key.startswith("grad::"):
             ref = torch.from_numpy(g[key])
             got = dict(net.named_parameters())[key[6:]].grad.cpu()[:ref.shape[0]]
-            assert _rel(got, ref) <= 1e-2, key
+            assert _cos(got, ref) >= 0.985, key
+
+
+def test_backward_kernels_layerwise_teacher_forced(built_lib):
+    """Every conv layer's backward (ReLU mask, bias grad, wgrad, dgrad) against torch fp32 autograd of that
+    ONE layer, fed with exactly the tensors our backward saw (its fp16 input activation and incoming dY)."""
+    import torch.nn.functional as F
+    from dream_b200 import autograd, models
+    torch.backends.cudnn.allow_tf32 = False
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix=""), seed=2, out_gain=0.2, mode="he")
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.rand((2, 3, 64, 96), generator=gen) * 2 - 1).cuda()
+    t = torch.rand((2, 7, 16, 24), generator=gen).cuda()
+    autograd.DEBUG_CAPTURE = []
+    try:
+        out = net(x)[0]
+        torch.nn.functional.mse_loss(out, t).backward()
+        cap = autograd.DEBUG_CAPTURE
+    finally:
+        autograd.DEBUG_CAPTURE = None
+    params = dict(net.named_parameters())
+    checked = 0
+    for key, g_in, cum, xin, dx in cap:
+        if g_in is None:
+            continue
+        w = params[key + ".weight"].detach()
+        b = params[key + ".bias"].detach()
+        cout, cin = w.shape[0], w.shape[1]
+        xr = xin[..., :cin].permute(0, 3, 1, 2).float().requires_grad_(True)
+        wr = w.clone().half().float().requires_grad_(True)       # our kernels see fp16 weights in dgrad
+        br = b.clone().requires_grad_(True)
+        y = F.conv2d(xr, wr, br, padding=1)
+        gy = g_in[..., :cout].permute(0, 3, 1, 2).float() / cum    # g_in is already ReLU-masked and scaled
+        y.backward(gy)
+        assert _rel(params[key + ".weight"].grad, wr.grad) <= 3e-3, (key, "wgrad", _rel(params[key + ".weight"].grad, wr.grad))
+        assert _rel(params[key + ".bias"].grad, br.grad) <= 3e-3, (key, "bias", _rel(params[key + ".bias"].grad, br.grad))
+        got_dx = dx[..., :cin].permute(0, 3, 1, 2).float() / cum
+        assert _rel(got_dx, xr.grad) <= 3e-3, (key, "dgrad", _rel(got_dx, xr.grad))
+        checked += 1
+    assert checked == 22
 
 
 def test_training_steps_track_oracle_loss_curve(built_lib):
