@@ -113,7 +113,7 @@ class _HourglassTrainFn(torch.autograd.Function):
                     g_in = g
                     g = ops.conv_taps(g, wd, None, taps, H, W)
                     if DEBUG_CAPTURE is not None:
-                        DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g))
+                        DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))   # g is re-scaled in place later
                 if kind == "first" and DEBUG_CAPTURE is not None:
                     DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None))
             elif kind == "pool":

@@ -39,134 +39,178 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 
 // One output tile (128 accumulator rows x BLOCK_N columns) of the NHWC fp16 path; called by the 4 epilogue
-// warps (128 threads, named barrier 1).  `t_row` = TMEM address of this thread's lane quarter / accumulator stage.
+// warps (128 threads, named barrier 1).  `t_row` = TMEM address of this thread's lane quarter / accumulator stage,
+// `smem_bias` = shared-memory copy of the current channel tile's fp32 bias (BLOCK_N floats, zeros when none).
+// Per 64-column chunk: TMEM -> registers -> +bias (+residuals) -> ReLU -> fp16 (the accumulator stage is handed
+// back to the MMA warp right after the last TMEM read, BEFORE any wait on the staging buffers) -> staging smem
+// (128B-swizzled) -> TMA store.  The fused 2x2 max pool runs on the packed fp16 values with warp shuffles when
+// the tile is 8 or 16 pixels wide (window partners are lanes ^1 and ^tw), else through a second smem pass.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
-                                                   uint32_t tempty_bar_addr, int n, int tx, int ty, int b, int ox,
-                                                   int oy, bool valid, int row, int lane, int epi_tid,
-                                                   uint32_t& chunk_ctr) {
-    const __half* res_row = nullptr;
-    const float* res32_row = nullptr;
-    float* y32_row = nullptr;
-    const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
-    if (p.residual != nullptr && valid) res_row = p.residual + row_off;
-    if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
-    if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
+                                                   uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
+                                                   int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
+                                                   int lane, int epi_tid, uint32_t& chunk_ctr) {
+  if (p.n_tiles > 1) {
+    // several output-channel tiles per CTA: re-stage this tile's BLOCK_N bias values (smem holds one tile's worth)
+    named_bar_sync(1, 128);
+    for (int i = epi_tid; i < BLOCK_N; i += 128)
+      smem_bias_gen[i] = p.bias != nullptr ? __ldg(p.bias + n * BLOCK_N + i) : 0.0f;
+    named_bar_sync(1, 128);
+  }
+  const __half* res_row = nullptr;
+  const float* res32_row = nullptr;
+  float* y32_row = nullptr;
+  const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
+  if (p.residual != nullptr && valid) res_row = p.residual + row_off;
+  if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
+  if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
+  const bool shfl_pool = p.pool && (p.tw == 8 || p.tw == 16);
+  const bool write_full = !p.pool || p.store_full || !shfl_pool;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
-      const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
-      const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
-      if (epi_tid == 0) {                            // stores that used obuf / pbuf two chunks ago have read them
-        if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+  for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
+    const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
+    const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
+    uint32_t hv[32];                                   // 64 output channels of this pixel, packed fp16
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
+      tmem_wait_ld();
+      float f[32];
+      const uint32_t bias_addr = smem_bias + (uint32_t)(c * 64 + h * 32) * 4u;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float b0, b1, b2, b3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_addr + (uint32_t)i * 4u));
+        f[i] = __uint_as_float(v[i]) + b0;
+        f[i + 1] = __uint_as_float(v[i + 1]) + b1;
+        f[i + 2] = __uint_as_float(v[i + 2]) + b2;
+        f[i + 3] = __uint_as_float(v[i + 3]) + b3;
       }
-      named_bar_sync(1, 128);
+      if (res_row != nullptr) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
-        tmem_wait_ld();
-        const int ch0 = n * BLOCK_N + c * 64 + h * 32;
-        float f[32];
+        for (int i = 0; i < 32; i += 8) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64 + h * 32 + i));
+          const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + i));
-            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+          for (int j = 0; j < 4; ++j) {
+            const float2 rf = __half22float2(rh[j]);
+            f[i + 2 * j] += rf.x;
+            f[i + 2 * j + 1] += rf.y;
           }
         }
-        if (res_row != nullptr) {
+      }
+      if (res32_row != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64 + h * 32 + i));
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 rf = __half22float2(rh[j]);
-              f[i + 2 * j] += rf.x;
-              f[i + 2 * j + 1] += rf.y;
-            }
-          }
+        for (int i = 0; i < 32; i += 4) {
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
+          f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
         }
-        if (res32_row != nullptr) {
+      }
+      if (p.relu) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
-            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-          }
-        }
-        if (p.relu) {
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+      }
+      if (y32_row != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-        }
-        if (y32_row != nullptr) {
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      }
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) =
-                make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-        }
+      for (int i = 0; i < 16; ++i) hv[h * 16 + i] = pack_h2(f[2 * i], f[2 * i + 1]);
+    }
+    if (c == BLOCK_N / 64 - 1) {
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar_addr);
+    }
+    if (epi_tid == 0) {                                // stores that used obuf / pbuf two chunks ago have read them
+      if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+    }
+    named_bar_sync(1, 128);
+    if (write_full) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t w0 = pack_h2(f[8 * j + 0], f[8 * j + 1]);
-          const uint32_t w1 = pack_h2(f[8 * j + 2], f[8 * j + 3]);
-          const uint32_t w2 = pack_h2(f[8 * j + 4], f[8 * j + 5]);
-          const uint32_t w3 = pack_h2(f[8 * j + 6], f[8 * j + 7]);
-          const uint32_t chunk16 = (uint32_t)(h * 4 + j) ^ (uint32_t)(row & 7);
-          const uint32_t dst = obuf + (uint32_t)row * 128u + chunk16 * 16u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1),
-                       "r"(w2), "r"(w3)
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = obuf + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) * 16u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hv[4 * j]), "r"(hv[4 * j + 1]),
+                     "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3])
+                     : "memory");
+      }
+    }
+    if (shfl_pool) {
+      // 2x2 window = lanes {l, l^1, l^tw, l^tw^1}; the even-x / even-y lane keeps the maximum
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        __half2 m = *reinterpret_cast<__half2*>(&hv[i]);
+        uint32_t o = __shfl_xor_sync(0xffffffffu, hv[i], 1);
+        m = __hmax2(m, *reinterpret_cast<__half2*>(&o));
+        uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
+        o = __shfl_xor_sync(0xffffffffu, mm, p.tw);
+        m = __hmax2(m, *reinterpret_cast<__half2*>(&o));
+        hv[i] = *reinterpret_cast<uint32_t*>(&m);
+      }
+      if ((lane & 1) == 0 && (lane & p.tw) == 0) {
+        const int ly = row / p.tw, lx = row - ly * p.tw;
+        const int pr = (ly >> 1) * (p.tw >> 1) + (lx >> 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)j ^ (uint32_t)(pr & 7)) * 16u);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hv[4 * j]), "r"(hv[4 * j + 1]),
+                       "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3])
                        : "memory");
-        }
-      }
-      if (c == BLOCK_N / 64 - 1) {
-        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar_addr);
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (epi_tid == 0 && (!p.pool || p.store_full)) {
-        tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
-        tma_store_commit();
-      }
-      if (p.pool) {
-        // 2x2 max over the tile that now sits in obuf: pooled row pr, 16 B chunk ch per work item
-        const int ptw = p.tw >> 1;
-        const int items = ptw * (p.th >> 1) * 8;
-        for (int item = epi_tid; item < items; item += 128) {
-          const int pr = item >> 3, ch = item & 7;
-          const int py = pr / ptw, px = pr - py * ptw;
-          const int r00 = (2 * py) * p.tw + 2 * px;
-          __half2 m[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = r00 + (k >> 1) * p.tw + (k & 1);
-            uint32_t a0, a1, a2, a3;
-            const uint32_t src = obuf + (uint32_t)r * 128u + (((uint32_t)ch ^ (uint32_t)(r & 7)) * 16u);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src) : "memory");
-            const __half2 h0 = *reinterpret_cast<__half2*>(&a0), h1 = *reinterpret_cast<__half2*>(&a1);
-            const __half2 h2 = *reinterpret_cast<__half2*>(&a2), h3 = *reinterpret_cast<__half2*>(&a3);
-            if (k == 0) { m[0] = h0; m[1] = h1; m[2] = h2; m[3] = h3; }
-            else { m[0] = __hmax2(m[0], h0); m[1] = __hmax2(m[1], h1); m[2] = __hmax2(m[2], h2); m[3] = __hmax2(m[3], h3); }
-          }
-          const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)ch ^ (uint32_t)(pr & 7)) * 16u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                       "r"(*reinterpret_cast<uint32_t*>(&m[0])), "r"(*reinterpret_cast<uint32_t*>(&m[1])),
-                       "r"(*reinterpret_cast<uint32_t*>(&m[2])), "r"(*reinterpret_cast<uint32_t*>(&m[3]))
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * ptw, ty * (p.th >> 1), b);
-          tma_store_commit();
         }
       }
     }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (epi_tid == 0 && (!p.pool || p.store_full)) {
+      tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
+      tma_store_commit();
+    }
+    if (p.pool && !shfl_pool) {
+      // generic tile shape: 2x2 max over the tile that now sits in obuf (pooled row pr, 16 B chunk ch per item)
+      const int ptw = p.tw >> 1;
+      const int items = ptw * (p.th >> 1) * 8;
+      for (int item = epi_tid; item < items; item += 128) {
+        const int pr = item >> 3, ch = item & 7;
+        const int py = pr / ptw, px = pr - py * ptw;
+        const int r00 = (2 * py) * p.tw + 2 * px;
+        __half2 m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = r00 + (k >> 1) * p.tw + (k & 1);
+          uint32_t a0, a1, a2, a3;
+          const uint32_t src = obuf + (uint32_t)r * 128u + (((uint32_t)ch ^ (uint32_t)(r & 7)) * 16u);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src) : "memory");
+          const __half2 h0 = *reinterpret_cast<__half2*>(&a0), h1 = *reinterpret_cast<__half2*>(&a1);
+          const __half2 h2 = *reinterpret_cast<__half2*>(&a2), h3 = *reinterpret_cast<__half2*>(&a3);
+          if (k == 0) { m[0] = h0; m[1] = h1; m[2] = h2; m[3] = h3; }
+          else { m[0] = __hmax2(m[0], h0); m[1] = __hmax2(m[1], h1); m[2] = __hmax2(m[2], h2); m[3] = __hmax2(m[3], h3); }
+        }
+        const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)ch ^ (uint32_t)(pr & 7)) * 16u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                     "r"(*reinterpret_cast<uint32_t*>(&m[0])), "r"(*reinterpret_cast<uint32_t*>(&m[1])),
+                     "r"(*reinterpret_cast<uint32_t*>(&m[2])), "r"(*reinterpret_cast<uint32_t*>(&m[3]))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+    }
+    if (p.pool && epi_tid == 0) {
+      tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * (p.tw >> 1), ty * (p.th >> 1), b);
+      tma_store_commit();
+    }
+  }
+}
+
+// Cooperative copy of the first output-channel tile's fp32 bias into shared memory (call before the prologue
+// __syncthreads(); layers with a single channel tile never touch it again).
+__device__ __forceinline__ void stage_bias(const ConvParams& p, float* sb, int block_n) {
+  for (int i = threadIdx.x; i < block_n; i += blockDim.x) sb[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
 }
 
 }  // namespace db200

@@ -58,6 +58,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t wbar = misc + 32u;
   const uint32_t tmem_ptr_smem = misc + 40u;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  const uint32_t smem_bias = misc + 64u;                                // BLOCK_N fp32
+  float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
+  stage_bias(p, smem_bias_gen, BLOCK_N);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -183,7 +186,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, tempty_bar(acc), n, tx, ty, b, ox, oy,
+      epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen, tempty_bar(acc), n, tx, ty, b, ox, oy,
                                   valid, row, lane, epi_tid, chunk_ctr);
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
@@ -223,7 +226,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   constexpr int kBBytes = BLOCK_N * 128;
   const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
   RsExtra x;
-  int budget = 232448 - 1024 - out_bytes - 1024;
+  int budget = 232448 - 1024 - out_bytes - 1024 - BLOCK_N * 4;
   if (RESIDENT) {
     budget -= 9 * p.kchunks * kBBytes;
     x.sa = budget / kSlabBytes;
@@ -235,7 +238,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     if (x.sb > 12) x.sb = 12;
   }
   DB_REQUIRE(x.sa >= 3 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs: shared memory budget too small");
-  const int smem_bytes = 1024 + x.sa * kSlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBBytes + out_bytes + 1024;
+  const int smem_bytes = 1024 + x.sa * kSlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBBytes + out_bytes + 1024 + BLOCK_N * 4;
 
   CUtensorMap tmA, tmB, tmC, tmP;
   memset(&tmC, 0, sizeof(tmC));

@@ -53,6 +53,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 4);
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  const uint32_t smem_bias = bar_base + 256u;                           // BLOCK_N fp32 (NHWC mode)
+  float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
+  if (OUT_MODE == DREAMB200_OUT_NHWC_F16) stage_bias(p, smem_bias_gen, BLOCK_N);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
-        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, tempty_bar(as), n, tx, ty, b, ox, oy,
+        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen, tempty_bar(as), n, tx, ty, b, ox, oy,
                                     valid, row, lane, epi_tid, chunk_ctr);
       } else {
         // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
@@ -294,12 +297,12 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   constexpr int kStageBytes = kABytes + BLOCK_N * 128;
   const int out_bytes =
       (OUT_MODE == DREAMB200_OUT_NHWC_F16) ? 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0) : 0;
-  const int budget = 232448 - 1024 - out_bytes - 512;
+  const int budget = 232448 - 1024 - out_bytes - 256 - BLOCK_N * 4;
   int stages = budget / kStageBytes;
   if (stages > 8) stages = 8;
   DB_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 stages");
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * kStageBytes + out_bytes + 512;
+  const int smem_bytes = 1024 + stages * kStageBytes + out_bytes + 256 + BLOCK_N * 4;
 
   // A: activation NHWC (C, W, H, B); box (64, tw, th, 1); element stride = conv stride
   CUtensorMap tmA, tmB, tmC, tmP;

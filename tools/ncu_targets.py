@@ -1,0 +1,41 @@
+"""Single-kernel targets for `ncu --set full`: python tools/ncu_targets.py <target> [batch].
+Each target launches its kernel 3 times on BASELINE-shaped tensors (profile the 3rd: --launch-skip 2 -c 1)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dream_b200 import ops
+
+target = sys.argv[1]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def conv_case(H, W, Cin, Cout, pool=None):
+    x = (torch.randn((B, H, W, Cin), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((Cout, Cin, 3, 3), device="cuda", generator=g) * (1.0 / (Cin * 9) ** 0.5)
+    rs = [(r, s) for r in range(3) for s in range(3)]
+    wp, bp = ops.pack_conv_weight(w, rs), ops.pad_bias(None, ops.round_up(Cout, 64), "cuda")
+    for _ in range(3):
+        ops.conv_taps(x, wp, bp, ops.TAPS_3x3, H, W, relu=True, pool=pool)
+
+
+if target == "conv256":            # layer_0_3_down.12/.14: 256->256 @100x100 (conv_tc_kernel<256,0>), 5.9 GMAC/img
+    conv_case(100, 100, 256, 256)
+elif target == "conv512":          # layer_0_4_down.21..25: 512->512 @50x50
+    conv_case(50, 50, 512, 512)
+elif target == "rs64":             # layer_0_1_down.2: 64->64 @400x400 + fused pool (conv_rs_kernel<64,true>)
+    conv_case(400, 400, 64, 64, pool="only")
+elif target == "rs128":            # layer_0_2_down.7: 128->128 @200x200 + fused pool (conv_rs_kernel<128,false>)
+    conv_case(200, 200, 128, 128, pool="only")
+elif target == "first":            # layer_0_1_down.0 fused with the input pack (first_conv_kernel)
+    x = torch.rand((B, 3, 400, 400), device="cuda", generator=g) * 2 - 1
+    w = torch.randn((64, 3, 3, 3), device="cuda", generator=g) * 0.2
+    wp, bp = ops.pack_first_weight(w, 64), ops.pad_bias(None, 64, "cuda")
+    for _ in range(3):
+        ops.first_conv3x3(x, wp, bp)
+elif target == "wgrad256":
+    x = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
+    dy = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
+    for _ in range(3):
+        ops.wgrad(dy, x, ops.TAPS_3x3)
+torch.cuda.synchronize()
