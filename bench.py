@@ -284,8 +284,21 @@ def main():
         dt, df, dn = fam[dom]
         achieved = df / dt / 1e9                       # TFLOP/s (flops / ms / 1e9)
         peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
+        traffic, traffic_note = None, None
+        prof = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+        if dom == "conv_tc<256>" and os.path.exists(prof):
+            try:
+                c = json.load(open(prof))["r01_conv256.ncu-rep"]
+                unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                rd, ru = c["dram_read"].split(); wr, wu = c["dram_write"].split()
+                traffic = float(rd) * unit[ru] + float(wr) * unit[wu]
+                traffic_note = ("dram__bytes_read+write of ONE conv_tc<256> launch (256->256 @100x100, B=128) from "
+                                "profiles/r01_ncu_full_summary.json; algorithmic bytes of that launch = 1.312e9 "
+                                "(fp16 in + out + weights)")
+            except Exception:
+                pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_kind": "bf16 dense sustained, " + peaks["source"],
                 "launches_per_step": dn // reps, "kernel_ms_per_step": dt / reps,
                 "kernel_share_of_conv_time": dt / reps / total_ms,

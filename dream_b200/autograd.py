@@ -28,9 +28,12 @@ DEBUG_CAPTURE = None
 def _dgrad_pack(weight, cin_pad, cout_pad):
     """Weights for the data gradient of a 3x3 'same' conv: dX[q] = sum_rs dY[q-(r-1,s-1)] W[:,:,r,s]^T."""
     wt = weight.detach().permute(1, 0, 2, 3)          # [Cin, Cout, 3, 3]: "output" channels are Cin now
-    rs = [(r, s) for r in range(3) for s in range(3)]
+    # kernel taps visited in reverse so the input offsets (1-r, 1-s) come out in the standard 3x3 order
+    # (-1,-1)..(1,1): the data gradient then qualifies for the same kernels as a forward 3x3 conv
+    rs = [(2 - r, 2 - s) for r in range(3) for s in range(3)]
     w = ops.pack_conv_weight(wt, rs, cin_pad=cout_pad, cout_pad=cin_pad)
     taps = [(1 - r, 1 - s) for r, s in rs]
+    assert taps == ops.TAPS_3x3
     return w, taps
 
 
