@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def finish(self):
         self._halt.set()
@@ -135,8 +135,14 @@ def run_reference(args):
         return
     import torch
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     n = 8
+    # all host threads it can use: logical CPUs or physical cores (SMT often hurts oneDNN convs) -- keep the faster
+    best = None
+    for thr_try in sorted({cores, max(1, cores // 2)}, reverse=True):
+        r, _, _, _ = cpu_baseline_sample(2, threads=thr_try)
+        if best is None or r > best[0]:
+            best = (r, thr_try)
+    torch.set_num_threads(best[1])
     rates, times = [], []
     for i in range(args.warmup_ref + args.steps_ref):
         r, tf, tp, thr = cpu_baseline_sample(n)
@@ -162,7 +168,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None)
@@ -217,30 +223,39 @@ def main():
             table = image_proc.find_peaks_device(belief, offset)
             return image_proc.select_keypoints_device(table, 0.25)
 
-    def step_e2e(i):
+    # e2e: the public input pipeline (dream_b200.pipeline) around DreamNetwork.inference / .train: host (pinned)
+    # batches in, keypoints (or the loss value) back on the host, H2D of step i+1 overlapped with step i.
+    from dream_b200 import pipeline
+
+    def run_e2e(steps):
         if mode == "train":
-            x = host_x[i & 1].to(dev, non_blocking=True)
-            t = host_t[i & 1].to(dev, non_blocking=True)
-            return net.train([x], t).item()         # the loss read-back train_network.py:507 does every step
-        with torch.no_grad():
-            x = host_x[i & 1].to(dev, non_blocking=True)
-            _, kps = net.inference(x)               # ends with the D2H copy of the keypoints
-            return kps
+            batches = ((host_x[i & 1], host_t[i & 1]) for i in range(steps))
+            for loss in pipeline.train_stream(net, batches):
+                loss.item()                          # the loss read-back train_network.py:507 does every step
+        else:
+            for _, kps in pipeline.inference_stream(net, (host_x[i & 1] for i in range(steps))):
+                pass                                 # kps is already on the host (D2H inside inference)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
+    def timed(fn, steps, warmup, whole=False):
+        if whole:
+            fn(warmup)
+        else:
+            for i in range(warmup):
+                fn(i)
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
-        for i in range(steps):
-            fn(i)
+        if whole:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -257,23 +272,24 @@ def main():
     ms, launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.finish() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
-    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, _ = timed(run_e2e, args.steps, args.warmup, whole=True)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- instrumented pass: per-launch CUDA-event durations of the tensor-core conv kernels ----
     roof = None
+    # every rank runs the instrumented steps (training steps contain a collective); rank 0 reports
+    ops.PROFILE = []
+    reps = 3
+    for i in range(reps):
+        step_device(i)
+    torch.cuda.synchronize()
+    profile_records, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
         peaks = _peaks()
-        ops.PROFILE = []
-        reps = 3
-        for i in range(reps):
-            step_device(i)
-        torch.cuda.synchronize()
         recs = {}
-        for tag, flops, e0, e1 in ops.PROFILE:
+        for tag, flops, e0, e1 in profile_records:
             r = recs.setdefault(tag, [0.0, 0.0, 0])
             r[0] += e0.elapsed_time(e1); r[1] += flops; r[2] += 1
-        ops.PROFILE = None
         total_ms = sum(r[0] for r in recs.values()) / reps
         fam = {}
         for tag, (t, f, n) in recs.items():

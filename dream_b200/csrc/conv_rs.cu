@@ -23,20 +23,43 @@ int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint6
 int device_sm_count();
 
 constexpr int kRsTw = 8, kRsTh = 16;
-constexpr int kSlabBytes = 18 * 1024;   // 18 image rows x 8 pixels x 128 B
 
 struct RsExtra {
   int sa, sb;        // ring depths: activation slabs, weight tiles
 };
 
-template <int BLOCK_N, bool RESIDENT>
+// UMMA descriptor, K-major SWIZZLE_128B, with an explicit stride between 8-row groups (SBO).  The hardware
+// applies the 128B swizzle to the computed shared-memory address, so a start address that is a multiple of 128 B
+// (not of 1024 B) still reads what TMA wrote -- that is what lets the HALO variant shift by one pixel.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// SUBTILES: 1 or 2 vertically adjacent 8x16 output tiles per CTA step; they share every weight tile (halves the
+//           weight traffic per MMA) and one activation slab of 16*SUBTILES+2 image rows.
+// HALO    : one slab of 10 pixels x (rows) per channel chunk serves all 9 taps (row pitch 1280 B, horizontal tap s
+//           = +128 B on the start address) instead of one 8-pixel slab per horizontal tap.
+template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                const __grid_constant__ ConvParams p, const __grid_constant__ RsExtra x) {
   constexpr int kBBytes = BLOCK_N * 128;
-  constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : 256;
+  constexpr int kRows = kRsTh * SUBTILES + 2;                            // image rows per slab
+  constexpr int kPitch = HALO ? 1280 : 1024;                             // bytes per image row inside a slab
+  constexpr int kSlabBytes = ((kRows * kPitch + 1023) / 1024) * 1024;
+  constexpr int kSlabTx = kRows * kPitch;                                // bytes TMA delivers per slab
+  constexpr int kSlabsPerChunk = HALO ? 1 : 3;
+  constexpr int kAccCols = 2 * SUBTILES * BLOCK_N;
+  constexpr int kTmemCols = kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
   constexpr uint32_t kIdesc = umma_idesc_f16_m128(BLOCK_N);
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -70,7 +93,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < sa; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * SUBTILES); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -97,13 +120,15 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int tx = t % p.tiles_x; t /= p.tiles_x;
         int ty = t % p.tiles_y;
         int b = t / p.tiles_y;
-        const int x0 = tx * kRsTw, y0 = ty * kRsTh;
+        const int x0 = tx * kRsTw, y0 = ty * kRsTh * SUBTILES;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int s = 0; s < 3; ++s) {
-            mbar_wait(aempty(as_), aph ^ 1u);
-            mbar_expect_tx(afull(as_), (uint32_t)kSlabBytes);
-            tma_load_4d(smem_a + as_ * kSlabBytes, &tmA, afull(as_), kc * 64, x0 - 1 + s, y0 - 1, b);
-            if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+            if (!HALO || s == 0) {
+              mbar_wait(aempty(as_), aph ^ 1u);
+              mbar_expect_tx(afull(as_), (uint32_t)kSlabTx);
+              tma_load_4d(smem_a + as_ * kSlabBytes, &tmA, afull(as_), kc * 64, x0 - 1 + (HALO ? 0 : s), y0 - 1, b);
+              if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+            }
             if (!RESIDENT) {
               for (int r = 0; r < 3; ++r) {
                 mbar_wait(bempty(bs_), bph ^ 1u);
@@ -128,13 +153,16 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SUBTILES * BLOCK_N);
         uint32_t first = 1u;
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          uint32_t slab = 0;
           for (int s = 0; s < 3; ++s) {
-            mbar_wait(afull(as_), aph);
-            tc_fence_after();
-            const uint32_t slab = smem_a + as_ * kSlabBytes;
+            if (!HALO || s == 0) {
+              mbar_wait(afull(as_), aph);
+              tc_fence_after();
+              slab = smem_a + as_ * kSlabBytes;
+            }
             for (int r = 0; r < 3; ++r) {
               uint32_t btile;
               if (RESIDENT) {
@@ -144,20 +172,27 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 btile = smem_b + bs_ * kBBytes;
               }
-              const uint64_t adesc = umma_desc_k_sw128(slab + r * 1024);   // vertical tap = row-group offset
               const uint64_t bdesc = umma_desc_k_sw128(btile);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, first ? 0u : 1u);
-                first = 0u;
+              for (int sub = 0; sub < SUBTILES; ++sub) {
+                // vertical tap = image-row offset; horizontal tap (HALO only) = one pixel = 128 B
+                const uint32_t a_addr = slab + (uint32_t)((r + sub * kRsTh) * kPitch) + (HALO ? (uint32_t)s * 128u : 0u);
+                const uint64_t adesc = umma_desc_k_sw128_sbo(a_addr, kPitch);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d_tmem + (uint32_t)(sub * BLOCK_N), adesc + 2u * k, bdesc + 2u * k, kIdesc,
+                           (first && k == 0) ? 0u : 1u);
               }
+              first = 0u;
               if (!RESIDENT) {
                 umma_commit(bempty(bs_));
                 if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
               }
             }
-            umma_commit(aempty(as_));
-            if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+            if (!HALO || s == 2) {
+              umma_commit(aempty(as_));
+              if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+            }
           }
         }
         umma_commit(tfull_bar(acc));
@@ -181,13 +216,18 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int tx = t % p.tiles_x; t /= p.tiles_x;
       int ty = t % p.tiles_y;
       int b = t / p.tiles_y;
-      const int ox = tx * kRsTw + lx, oy = ty * kRsTh + ly;
-      const bool valid = (ox < p.Wo) && (oy < p.Ho);
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen, tempty_bar(acc), n, tx, ty, b, ox, oy,
-                                  valid, row, lane, epi_tid, chunk_ctr);
+#pragma unroll 1
+      for (int sub = 0; sub < SUBTILES; ++sub) {
+        const int tys = ty * SUBTILES + sub;                  // 16-row tile index of this sub-tile
+        const int ox = tx * kRsTw + lx, oy = tys * kRsTh + ly;
+        const bool valid = (ox < p.Wo) && (oy < p.Ho);
+        const uint32_t t_row =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
+        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+                                    tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid, chunk_ctr);
+      }
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
     }
@@ -201,13 +241,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BLOCK_N, bool RESIDENT>
+template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO>
 static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.tw = kRsTw; p.th = kRsTh;
   p.tiles_x = (d->Wo + kRsTw - 1) / kRsTw;
-  p.tiles_y = (d->Ho + kRsTh - 1) / kRsTh;
+  p.tiles_y = (d->Ho + kRsTh * SUBTILES - 1) / (kRsTh * SUBTILES);
   p.n_tiles = d->Cout_pad / BLOCK_N;
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * d->B;
@@ -224,6 +264,9 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.store_full = d->y != nullptr ? 1 : 0;
 
   constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kRows = kRsTh * SUBTILES + 2;
+  constexpr int kPitch = HALO ? 1280 : 1024;
+  constexpr int kSlabBytes = ((kRows * kPitch + 1023) / 1024) * 1024;
   const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
   RsExtra x;
   int budget = 232448 - 1024 - out_bytes - 1024 - BLOCK_N * 4;
@@ -233,12 +276,16 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     if (x.sa > 8) x.sa = 8;
     x.sb = 1;
   } else {
-    x.sa = 4;
+    // split the budget between the two rings in proportion to what one channel chunk consumes
+    const int a_need = (HALO ? 1 : 3) * kSlabBytes, b_need = 9 * kBBytes;
+    x.sa = (int)((long long)budget * a_need / (a_need + b_need)) / kSlabBytes;
+    if (x.sa < (HALO ? 2 : 3)) x.sa = HALO ? 2 : 3;
     x.sb = (budget - x.sa * kSlabBytes) / kBBytes;
     if (x.sb > 12) x.sb = 12;
   }
-  DB_REQUIRE(x.sa >= 3 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs: shared memory budget too small");
-  const int smem_bytes = 1024 + x.sa * kSlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBBytes + out_bytes + 1024 + BLOCK_N * 4;
+  DB_REQUIRE(x.sa >= 2 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs: shared memory budget too small");
+  const int smem_bytes =
+      1024 + x.sa * kSlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBBytes + out_bytes + 1024 + BLOCK_N * 4;
 
   CUtensorMap tmA, tmB, tmC, tmP;
   memset(&tmC, 0, sizeof(tmC));
@@ -246,7 +293,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-    uint32_t box[4] = {64, kRsTw, kRsTh + 2, 1};
+    uint32_t box[4] = {64, HALO ? 10u : 8u, (uint32_t)kRows, 1};
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es, "rs activation")) return -1;
   }
@@ -272,7 +319,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "rs output")) return -1;
   }
-  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT>;
+  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -284,6 +331,11 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 // Returns 1 and launches when the layer qualifies for the row-shared kernel, 0 when conv_tc should handle it,
@@ -302,13 +354,24 @@ int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   const double util = (double)d->Wo * d->Ho /
                       ((double)((d->Wo + kRsTw - 1) / kRsTw) * ((d->Ho + kRsTh - 1) / kRsTh) * 128.0);
   if (util < min_util) return 0;
+  // variants (env overrides are for A/B measurements): DREAMB200_RS_PAIR: two stacked tiles share each weight
+  // tile (streamed-weight layers); DREAMB200_RS_HALO: one 10-pixel slab serves all horizontal taps.
+  static const int pair = env_flag("DREAMB200_RS_PAIR", 1);
+  static const int halo = env_flag("DREAMB200_RS_HALO", 0);
   int rc;
   if (d->Cout_pad % 128 == 0) {
-    rc = launch_rs<128, false>(d, stream);
+    if (pair && halo) rc = launch_rs<128, false, 2, true>(d, stream);
+    else if (pair) rc = launch_rs<128, false, 2, false>(d, stream);
+    else if (halo) rc = launch_rs<128, false, 1, true>(d, stream);
+    else rc = launch_rs<128, false, 1, false>(d, stream);
   } else if (d->Cout_pad == 64 && d->Cin == 64) {
-    rc = launch_rs<64, true>(d, stream);
+    if (halo) rc = launch_rs<64, true, 1, true>(d, stream);
+    else rc = launch_rs<64, true, 1, false>(d, stream);
   } else {
-    rc = launch_rs<64, false>(d, stream);
+    if (pair && halo) rc = launch_rs<64, false, 2, true>(d, stream);
+    else if (pair) rc = launch_rs<64, false, 2, false>(d, stream);
+    else if (halo) rc = launch_rs<64, false, 1, true>(d, stream);
+    else rc = launch_rs<64, false, 1, false>(d, stream);
   }
   return rc == 0 ? 1 : rc;
 }

@@ -302,3 +302,26 @@ def test_missing_cpu_fallback_is_loud(built_lib):
     net = models.DreamHourglass(7, internalize_spatial_softmax=False).eval()
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 32, 32))
+
+
+def test_prefetching_pipeline_matches_direct_inference(built_lib):
+    """dream_b200.pipeline.inference_stream (H2D overlapped on a side stream) == DreamNetwork.inference."""
+    from conftest import panda_config
+    from dream_b200 import network, pipeline
+    cfg = panda_config("vgg")
+    cfg["training"]["config"]["net_input_resolution"] = [96, 64]
+    net = network.create_network_from_config_data(cfg)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=4, out_gain=13.0, mode="default")
+    net.model.load_state_dict(sd)
+    net.enable_evaluation()
+    gen = torch.Generator().manual_seed(2)
+    batches = [(torch.rand((3, 3, 64, 96), generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
+    direct = []
+    with torch.no_grad():
+        for x in batches:
+            b, k = net.inference(x.cuda())
+            direct.append((b.cpu(), k))
+    streamed = [(b.cpu(), k) for b, k in pipeline.inference_stream(net, batches)]
+    assert len(streamed) == 4
+    for (b0, k0), (b1, k1) in zip(direct, streamed):
+        assert torch.equal(b0, b1) and torch.equal(k0, k1)
