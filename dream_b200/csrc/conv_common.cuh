@@ -45,18 +45,23 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // back to the MMA warp right after the last TMEM read, BEFORE any wait on the staging buffers) -> staging smem
 // (128B-swizzled) -> TMA store.  The fused 2x2 max pool runs on the packed fp16 values with warp shuffles when
 // the tile is 8 or 16 pixels wide (window partners are lanes ^1 and ^tw), else through a second smem pass.
-template <int BLOCK_N>
+// SPLIT = 1: 4 epilogue warps, each thread handles all 64 columns of a chunk.  SPLIT = 2: 8 epilogue warps, two
+// per TMEM lane quarter, each thread handles 32 of the 64 columns (`hsel`) -- halves the per-tile epilogue latency
+// for the narrow layers where the epilogue, not the MMA, paces the tile.
+template <int BLOCK_N, int SPLIT = 1>
 __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
                                                    int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
-                                                   int lane, int epi_tid, uint32_t& chunk_ctr) {
+                                                   int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0) {
+  constexpr int kEpiThreads = 128 * SPLIT;
+  constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
     // several output-channel tiles per CTA: re-stage this tile's BLOCK_N bias values (smem holds one tile's worth)
-    named_bar_sync(1, 128);
-    for (int i = epi_tid; i < BLOCK_N; i += 128)
+    named_bar_sync(1, kEpiThreads);
+    for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads)
       smem_bias_gen[i] = p.bias != nullptr ? __ldg(p.bias + n * BLOCK_N + i) : 0.0f;
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kEpiThreads);
   }
   const __half* res_row = nullptr;
   const float* res32_row = nullptr;
@@ -71,9 +76,10 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
     const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
     const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
-    uint32_t hv[32];                                   // 64 output channels of this pixel, packed fp16
+    uint32_t hv[kRegs];                                // this thread's output channels of the pixel, packed fp16
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+      const int h = SPLIT == 2 ? hsel : hh;
       uint32_t v[32];
       tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
       tmem_wait_ld();
@@ -119,7 +125,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
           *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) hv[h * 16 + i] = pack_h2(f[2 * i], f[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) hv[hh * 16 + i] = pack_h2(f[2 * i], f[2 * i + 1]);
     }
     if (c == BLOCK_N / 64 - 1) {
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp right away
@@ -130,11 +136,12 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     if (epi_tid == 0) {                                // stores that used obuf / pbuf two chunks ago have read them
       if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
     }
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kEpiThreads);
+    const uint32_t j0 = SPLIT == 2 ? (uint32_t)hsel * 4u : 0u;      // first 16-byte chunk this thread owns
     if (write_full) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t dst = obuf + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) * 16u);
+      for (int j = 0; j < 8 / SPLIT; ++j) {
+        const uint32_t dst = obuf + (uint32_t)row * 128u + (((j0 + (uint32_t)j) ^ (uint32_t)(row & 7)) * 16u);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hv[4 * j]), "r"(hv[4 * j + 1]),
                      "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3])
                      : "memory");
@@ -143,7 +150,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     if (shfl_pool) {
       // 2x2 window = lanes {l, l^1, l^tw, l^tw^1}; the even-x / even-y lane keeps the maximum
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < kRegs; ++i) {
         __half2 m = *reinterpret_cast<__half2*>(&hv[i]);
         uint32_t o = __shfl_xor_sync(0xffffffffu, hv[i], 1);
         m = __hmax2(m, *reinterpret_cast<__half2*>(&o));
@@ -156,8 +163,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
         const int ly = row / p.tw, lx = row - ly * p.tw;
         const int pr = (ly >> 1) * (p.tw >> 1) + (lx >> 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((uint32_t)j ^ (uint32_t)(pr & 7)) * 16u);
+        for (int j = 0; j < 8 / SPLIT; ++j) {
+          const uint32_t dst = pbuf + (uint32_t)pr * 128u + (((j0 + (uint32_t)j) ^ (uint32_t)(pr & 7)) * 16u);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hv[4 * j]), "r"(hv[4 * j + 1]),
                        "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3])
                        : "memory");
@@ -165,7 +172,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kEpiThreads);
     if (epi_tid == 0 && (!p.pool || p.store_full)) {
       tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
       tma_store_commit();
@@ -174,7 +181,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       // generic tile shape: 2x2 max over the tile that now sits in obuf (pooled row pr, 16 B chunk ch per item)
       const int ptw = p.tw >> 1;
       const int items = ptw * (p.th >> 1) * 8;
-      for (int item = epi_tid; item < items; item += 128) {
+      for (int item = epi_tid; item < items; item += kEpiThreads) {
         const int pr = item >> 3, ch = item & 7;
         const int py = pr / ptw, px = pr - py * ptw;
         const int r00 = (2 * py) * p.tw + 2 * px;
@@ -198,7 +205,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                      : "memory");
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
     }
     if (p.pool && epi_tid == 0) {
       tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * (p.tw >> 1), ty * (p.th >> 1), b);

@@ -45,8 +45,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, ui
 //           weight traffic per MMA) and one activation slab of 16*SUBTILES+2 image rows.
 // HALO    : one slab of 10 pixels x (rows) per channel chunk serves all 9 taps (row pitch 1280 B, horizontal tap s
 //           = +128 B on the start address) instead of one 8-pixel slab per horizontal tap.
+constexpr int kRsEpiSplit = 2;                          // 8 epilogue warps (see conv_common.cuh)
+constexpr int kRsThreads = 64 + 128 * kRsEpiSplit;
+
 template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kRsThreads, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                const __grid_constant__ ConvParams p, const __grid_constant__ RsExtra x) {
@@ -93,7 +96,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < sa; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * SUBTILES); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * kRsEpiSplit * SUBTILES); }
     mbar_init(wbar, 1);
     fence_mbar_init();
   }
@@ -202,8 +205,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two per TMEM lane quarter, 32 columns each) =====================
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int epi_tid = threadIdx.x - 64;
     const int ly = row / kRsTw, lx = row - ly * kRsTw;
@@ -225,8 +229,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool valid = (ox < p.Wo) && (oy < p.Ho);
         const uint32_t t_row =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
-        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
-                                    tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid, chunk_ctr);
+        epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+                                                 tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid,
+                                                 chunk_ctr, hsel);
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
@@ -327,7 +332,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p, x);
+  kern<<<grid, kRsThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p, x);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -357,7 +362,7 @@ int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   // variants (env overrides are for A/B measurements): DREAMB200_RS_PAIR: two stacked tiles share each weight
   // tile (streamed-weight layers); DREAMB200_RS_HALO: one 10-pixel slab serves all horizontal taps.
   static const int pair = env_flag("DREAMB200_RS_PAIR", 1);
-  static const int halo = env_flag("DREAMB200_RS_HALO", 0);
+  static const int halo = env_flag("DREAMB200_RS_HALO", 1);
   int rc;
   if (d->Cout_pad % 128 == 0) {
     if (pair && halo) rc = launch_rs<128, false, 2, true>(d, stream);
