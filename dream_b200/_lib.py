@@ -53,6 +53,8 @@ _PROTOS = {
     "dreamb200_nhwc_to_cm_f16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
                         [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dreamb200_wgrad_deconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
+                               [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dreamb200_absmax_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),

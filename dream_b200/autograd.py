@@ -58,17 +58,28 @@ class _HourglassTrainFn(torch.autograd.Function):
                 y = models._run_conv(P[key], t)
                 tape.append(("conv", key, t, y))
                 t = y
-        stages = [("upsample_0_4", ".4", ".6"), ("upsample_0_3", ".4", ".6")]
-        if model.full_output:
-            stages += [("upsample_0_2", ".2", ".4"), ("upsample_0_1", ".2", ".4")]
-        for name, a, b in stages:
-            y = ops.upsample2(t)
-            tape.append(("up", None, t, y))
-            t = y
-            for suffix in (a, b):
-                y = models._run_conv(P[name + suffix], t)
-                tape.append(("conv", name + suffix, t, y))
+        if model.deconv_decoder:
+            # ConvTranspose2d(3, s2, p1, op1) + ReLU (+ conv3x3 + ReLU), models.py:618-686
+            for name in ("deconv_0_4", "deconv_0_3", "deconv_0_2", "deconv_0_1"):
+                y = models._run_deconv(P[name + ".0"], t)
+                tape.append(("deconv", name + ".0", t, y))
                 t = y
+                if name != "deconv_0_1":
+                    y = models._run_conv(P[name + ".2"], t)
+                    tape.append(("conv", name + ".2", t, y))
+                    t = y
+        else:
+            stages = [("upsample_0_4", ".4", ".6"), ("upsample_0_3", ".4", ".6")]
+            if model.full_output:
+                stages += [("upsample_0_2", ".2", ".4"), ("upsample_0_1", ".2", ".4")]
+            for name, a, b in stages:
+                y = ops.upsample2(t)
+                tape.append(("up", None, t, y))
+                t = y
+                for suffix in (a, b):
+                    y = models._run_conv(P[name + suffix], t)
+                    tape.append(("conv", name + suffix, t, y))
+                    t = y
         for key in ("heads_0.0", "heads_0.2"):
             y = models._run_conv(P[key], t)
             tape.append(("conv", key, t, y))
@@ -119,6 +130,27 @@ class _HourglassTrainFn(torch.autograd.Function):
                         DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))   # g is re-scaled in place later
                 if kind == "first" and DEBUG_CAPTURE is not None:
                     DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None))
+            elif kind == "deconv":
+                node = models._node_for(model, key)
+                pc = P[key]
+                f = torch.exp2(torch.floor(torch.log2(256.0 / ops.absmax(g).clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
+                ops.scale_mask_(g, yout if pc.relu else None, f)
+                cum = cum * f
+                inv = 1.0 / cum
+                cin, cout = node.weight.shape[0], node.weight.shape[1]          # ConvTranspose2d: [Cin, Cout, 3, 3]
+                if node.bias is not None:
+                    grads[key + ".bias"] = ops.bias_grad(g)[:cout] * inv
+                # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
+                dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
+                grads[key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
+                # dX[p] = sum_taps W[:, :, tap] dY[2p + tap-1]: a stride-2 3x3 conv over dY
+                rs = [(r, s_) for r in range(3) for s_ in range(3)]
+                wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
+                B, H, W, _ = xin.shape
+                g_in = g
+                g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2)
+                if DEBUG_CAPTURE is not None:
+                    DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))
             elif kind == "pool":
                 g = ops.maxpool2_bwd(xin, g)
             elif kind == "up":
@@ -128,10 +160,10 @@ class _HourglassTrainFn(torch.autograd.Function):
 
 
 def hourglass_train_forward(model, x):
-    if model.deconv_decoder or model.skip_connections:
+    if model.skip_connections:
         raise NotImplementedError(
-            "dream_b200 training currently covers the upsample-decoder DreamHourglass (vgg-Q family); "
-            "deconv_decoder / skip_connections training is not built yet (inference is).")
+            "dream_b200 training covers DreamHourglass with the upsample or the deconv decoder (vgg-Q / vgg-F); "
+            "skip_connections training is not built yet (inference is).")
     x = model._check_input(x)
     params = [p for _, p in model.named_parameters()]
     return _HourglassTrainFn.apply(model, x, *params)

@@ -23,8 +23,14 @@
 
 namespace db200 {
 
+// NHWC mode runs 8 epilogue warps (two per TMEM lane quarter, 32 of each chunk's 64 columns each): for layers with a
+// short K loop (1x1 convs, few input channels) the epilogue, not the MMA, paces a tile.  The fp32 NCHW head keeps 4.
+template <int OUT_MODE>
+__host__ __device__ constexpr int kTcThreads() { return OUT_MODE == DREAMB200_OUT_NHWC_F16 ? 64 + 256 : 64 + 128; }
+constexpr int kTcSplit = 2;
+
 template <int BLOCK_N, int OUT_MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTcThreads<OUT_MODE>(), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                const __grid_constant__ ConvParams p) {
@@ -73,7 +79,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), OUT_MODE == DREAMB200_OUT_NHWC_F16 ? 4 * kTcSplit : 4);
     }
     fence_mbar_init();
   }
@@ -144,8 +150,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9 NHWC / 2..5 NCHW head) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;       // which 32 of a chunk's 64 columns (NHWC mode)
     const int row = q * 32 + lane;          // accumulator row == output pixel inside the tile
     const int epi_tid = threadIdx.x - 64;
     const int ly = row / p.tw, lx = row - ly * p.tw;
@@ -166,8 +173,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
-        epilogue_nhwc_tile<BLOCK_N>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen, tempty_bar(as), n, tx, ty, b, ox, oy,
-                                    valid, row, lane, epi_tid, chunk_ctr);
+        epilogue_nhwc_tile<BLOCK_N, kTcSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+                                              tempty_bar(as), n, tx, ty, b, ox, oy, valid, row, lane, epi_tid,
+                                              chunk_ctr, hsel);
       } else {
         // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
         uint32_t v[16];
@@ -347,7 +355,7 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
     attr_set = true;
   }
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
+  kern<<<grid, kTcThreads<OUT_MODE>(), smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

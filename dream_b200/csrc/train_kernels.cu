@@ -42,6 +42,8 @@ struct WgradParams {
   float* dw;                // fp32 [taps][Cout_pad][Cin_pad], accumulated with atomics
   int Cout_pad, Cin_pad;
   int stages;
+  int a_stride;             // 1: conv (dY on X's grid); 2: ConvTranspose stride 2 (dY on the 2x finer grid)
+  int shift_a;              // tap offset applied to the dY coordinates (ConvTranspose) instead of X's
 };
 
 constexpr int kWgThreads = 192;
@@ -109,13 +111,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * kStageBytes;
         mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
+        const int ax = x0 * p.a_stride + (p.shift_a ? p.dx[tap] : 0), ay = y0 * p.a_stride + (p.shift_a ? p.dy[tap] : 0);
+        const int bx = x0 + (p.shift_a ? 0 : p.dx[tap]), by = y0 + (p.shift_a ? 0 : p.dy[tap]);
 #pragma unroll
         for (int m = 0; m < 2; ++m)
-          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, x0, y0, b);
+          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, ax, ay, b);
 #pragma unroll
         for (int n = 0; n < BLOCK_N / 64; ++n)
-          tma_load_4d(sa + kABytes + n * kChunkBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64,
-                      x0 + p.dx[tap], y0 + p.dy[tap], b);
+          tma_load_4d(sa + kABytes + n * kChunkBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, bx, by, b);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -377,14 +380,15 @@ static int grid_cap(long long work, int threads) {
 
 using namespace db200;
 
-extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
-                               int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
+static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, int W, int Hd, int Wd, int a_stride,
+                      int shift_a, int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                      cudaStream_t stream) {
   DB_REQUIRE(dy && x && dw && tap_dy && tap_dx, "wgrad: null pointer");
   DB_REQUIRE(Cout_pad % 64 == 0 && Cin_pad % 64 == 0, "wgrad: channel counts must be multiples of 64 (%d, %d)",
              Cout_pad, Cin_pad);
   DB_REQUIRE(taps >= 1 && taps <= DREAMB200_MAX_TAPS, "wgrad: taps=%d out of range", taps);
-  DB_REQUIRE(B > 0 && H > 0 && W > 0, "wgrad: empty input");
+  DB_REQUIRE(B > 0 && H > 0 && W > 0 && Hd > 0 && Wd > 0, "wgrad: empty input");
+  DB_REQUIRE(a_stride == 1 || a_stride == 2, "wgrad: a_stride=%d unsupported", a_stride);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;
@@ -393,6 +397,8 @@ extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, 
   p.taps = taps;
   memcpy(p.dy, tap_dy, taps);
   memcpy(p.dx, tap_dx, taps);
+  p.a_stride = a_stride;
+  p.shift_a = shift_a;
   const int block_n = Cin_pad % 128 == 0 ? 128 : 64;
   p.co_tiles = (Cout_pad + 127) / 128;   // a half-empty last tile is zero-filled by TMA
   p.ci_tiles = Cin_pad / block_n;
@@ -407,20 +413,35 @@ extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, 
   p.Cin_pad = Cin_pad;
 
   CUtensorMap tmDY, tmX;
-  const uint32_t box[4] = {64, kWgTw, kWgTh, 1};
-  const uint32_t es[4] = {1, 1, 1, 1};
   {
-    uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Cout_pad * 2, (uint64_t)W * Cout_pad * 2, (uint64_t)H * W * Cout_pad * 2};
+    const uint32_t s = (uint32_t)a_stride;
+    const uint32_t box[4] = {64, kWgTw * s, kWgTh * s, 1};
+    const uint32_t es[4] = {1, s, s, 1};
+    uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)Wd, (uint64_t)Hd, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cout_pad * 2, (uint64_t)Wd * Cout_pad * 2, (uint64_t)Hd * Wd * Cout_pad * 2};
     if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad dY")) return -1;
   }
   {
+    const uint32_t box[4] = {64, kWgTw, kWgTh, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
     uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
     if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad X")) return -1;
   }
   if (block_n == 128) return launch_wgrad<128>(tmDY, tmX, p, stream);
   return launch_wgrad<64>(tmDY, tmX, p, stream);
+}
+
+extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
+                               int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
+  return wgrad_impl(dy, x, dw, B, H, W, H, W, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx, (cudaStream_t)stream_v);
+}
+
+extern "C" int dreamb200_wgrad_deconv(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
+                                      int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                                      void* stream_v) {
+  return wgrad_impl(dy, x, dw, B, H, W, 2 * H, 2 * W, 2, 1, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
+                    (cudaStream_t)stream_v);
 }
 
 extern "C" int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream) {

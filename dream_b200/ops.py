@@ -234,11 +234,12 @@ def nhwc_to_cm(x):
     return y
 
 
-def wgrad(dy, x, taps):
-    """dW[tap][co][ci] = sum_p dy[p][co] * x[p + tap][ci]; dy/x NHWC fp16 of equal H, W -> fp32 [T,Co,Ci]."""
-    B, H, W_, Co = dy.shape
-    Ci = x.shape[3]
-    assert tuple(x.shape[:3]) == (B, H, W_)
+def wgrad(dy, x, taps, deconv=False):
+    """dW[tap][co][ci] = sum_p dy[p][co] * x[p + tap][ci]; dy/x NHWC fp16 of equal H, W -> fp32 [T,Co,Ci].
+    deconv=True: stride-2 ConvTranspose weight gradient, dy on the 2x finer grid: sum_p dy[2p + tap][co] * x[p][ci]."""
+    B, H, W_, Ci = x.shape
+    Co = dy.shape[3]
+    assert tuple(dy.shape[:3]) == ((B, 2 * H, 2 * W_) if deconv else (B, H, W_))
     assert dy.dtype == torch.float16 and x.dtype == torch.float16 and dy.is_contiguous() and x.is_contiguous()
     dw = torch.zeros((len(taps), Co, Ci), dtype=torch.float32, device=dy.device)
     tdy = (C.c_int8 * len(taps))(*[t[0] for t in taps])
@@ -247,8 +248,9 @@ def wgrad(dy, x, taps):
     if PROFILE is not None:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib().dreamb200_wgrad(_ptr(dy), _ptr(x), _ptr(dw), B, H, W_, Co, Ci, len(taps),
-                                C.cast(tdy, C.c_void_p), C.cast(tdx, C.c_void_p), _stream()), "dreamb200_wgrad")
+    fn = lib().dreamb200_wgrad_deconv if deconv else lib().dreamb200_wgrad
+    check(fn(_ptr(dy), _ptr(x), _ptr(dw), B, H, W_, Co, Ci, len(taps),
+             C.cast(tdy, C.c_void_p), C.cast(tdx, C.c_void_p), _stream()), "dreamb200_wgrad")
     if PROFILE is not None:
         e1.record()
         PROFILE.append(("wgrad_tc T%d Cin%d Cout%d %dx%d" % (len(taps), Ci, Co, H, W_),

@@ -105,6 +105,10 @@ int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C,
    dw fp32 [taps][Cout_pad][Cin_pad] (caller zeroes it); autograd of nn.Conv2d weights */
 int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
                     int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream);
+/* weight gradient of a stride-2 ConvTranspose2d (k3 p1 op1 / k4 p1; output 2H x 2W):
+   dW[tap][co][ci] += sum_pixels dY[2p + tap][co] * X[p][ci]; x [B,H,W,Cin_pad], dy [B,2H,2W,Cout_pad] */
+int dreamb200_wgrad_deconv(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
+                           int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream);
 /* dy = dy * (*scale) * (y > 0): autograd of nn.ReLU given its output, fused with the power-of-two
    re-scaling that keeps fp16 gradients in range; y and/or scale may be NULL */
 int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream);

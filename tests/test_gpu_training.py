@@ -123,22 +123,26 @@ def test_hourglass_gradients_match_oracle_and_golden(fixture, golden_dir, built_
             assert _cos(got, ref) >= 0.985, key
 
 
-def test_backward_kernels_layerwise_teacher_forced(built_lib):
-    """Every conv layer's backward (ReLU mask, bias grad, wgrad, dgrad) against torch fp32 autograd of that
-    ONE layer, fed with exactly the tensors our backward saw (its fp16 input activation and incoming dY)."""
+@pytest.mark.parametrize("arch", ["vgg_q", "vgg_f"])
+def test_backward_kernels_layerwise_teacher_forced(arch, built_lib):
+    """Every conv / deconv layer's backward (ReLU mask, bias grad, wgrad, dgrad) against torch fp32 autograd of
+    that ONE layer, fed with exactly the tensors our backward saw (its fp16 input activation and incoming dY)."""
     import torch.nn.functional as F
     from dream_b200 import autograd, models
     torch.backends.cudnn.allow_tf32 = False
-    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix=""), seed=2, out_gain=0.2, mode="he")
-    net = models.DreamHourglass(7, internalize_spatial_softmax=False)
+    kw = dict(deconv_decoder=True, full_output=True) if arch == "vgg_f" else {}
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix="", **kw), seed=2, out_gain=0.2, mode="he")
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False, **kw)
     net.load_state_dict(sd)
     net = net.cuda().train()
     gen = torch.Generator().manual_seed(3)
     x = (torch.rand((2, 3, 64, 96), generator=gen) * 2 - 1).cuda()
-    t = torch.rand((2, 7, 16, 24), generator=gen).cuda()
+    out_hw = (64, 96) if arch == "vgg_f" else (16, 24)
+    t = torch.rand((2, 7) + out_hw, generator=gen).cuda()
     autograd.DEBUG_CAPTURE = []
     try:
         out = net(x)[0]
+        assert tuple(out.shape) == tuple(t.shape)
         torch.nn.functional.mse_loss(out, t).backward()
         cap = autograd.DEBUG_CAPTURE
     finally:
@@ -150,11 +154,15 @@ def test_backward_kernels_layerwise_teacher_forced(built_lib):
             continue
         w = params[key + ".weight"].detach()
         b = params[key + ".bias"].detach()
-        cout, cin = w.shape[0], w.shape[1]
+        deconv = key.startswith("deconv_") and key.endswith(".0")
+        cin, cout = (w.shape[0], w.shape[1]) if deconv else (w.shape[1], w.shape[0])
         xr = xin[..., :cin].permute(0, 3, 1, 2).float().requires_grad_(True)
         wr = w.clone().half().float().requires_grad_(True)       # our kernels see fp16 weights in dgrad
         br = b.clone().requires_grad_(True)
-        y = F.conv2d(xr, wr, br, padding=1)
+        if deconv:
+            y = F.conv_transpose2d(xr, wr, br, stride=2, padding=1, output_padding=1)
+        else:
+            y = F.conv2d(xr, wr, br, padding=1)
         gy = g_in[..., :cout].permute(0, 3, 1, 2).float() / cum    # g_in is already ReLU-masked and scaled
         y.backward(gy)
         assert _rel(params[key + ".weight"].grad, wr.grad) <= 3e-3, (key, "wgrad", _rel(params[key + ".weight"].grad, wr.grad))
@@ -162,7 +170,30 @@ def test_backward_kernels_layerwise_teacher_forced(built_lib):
         got_dx = dx[..., :cin].permute(0, 3, 1, 2).float() / cum
         assert _rel(got_dx, xr.grad) <= 3e-3, (key, "dgrad", _rel(got_dx, xr.grad))
         checked += 1
-    assert checked == 22
+    assert checked == (25 if arch == "vgg_f" else 22)
+
+
+def test_vgg_f_training_gradients_track_oracle(built_lib):
+    """vgg-F (deconv decoder, full-resolution output): loss and gradient direction / norm vs the oracle's autograd."""
+    from dream_b200 import models
+    kw = dict(deconv_decoder=True, full_output=True)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix="", **kw), seed=6, out_gain=13.0, mode="default")
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand((2, 3, 48, 64), generator=gen) * 2 - 1
+    target = torch.rand((2, 7, 48, 64), generator=gen)
+    ref_loss, ref_grads, _ = _oracle_grads(sd, x, target, **kw)
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False, **kw)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    loss = torch.nn.MSELoss()(net(x.cuda())[0], target.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss) <= 1e-3 * ref_loss
+    for name, p in net.named_parameters():
+        got, ref = p.grad.cpu(), ref_grads[name]
+        assert _cos(got, ref) >= 0.985, (name, _cos(got, ref))
+        assert abs(float(got.norm() / ref.norm()) - 1.0) <= 0.03, (name, float(got.norm() / ref.norm()))
+        if name.startswith("heads_0"):
+            assert _rel(got, ref) <= 1e-2, (name, _rel(got, ref))
 
 
 def test_training_steps_track_oracle_loss_curve(built_lib):
