@@ -325,3 +325,39 @@ def test_prefetching_pipeline_matches_direct_inference(built_lib):
     assert len(streamed) == 4
     for (b0, k0), (b1, k1) in zip(direct, streamed):
         assert torch.equal(b0, b1) and torch.equal(k0, k1)
+
+
+def test_facade_single_image_and_checkpoint_round_trip(tmp_path, built_lib):
+    """keypoints_from_image (network.py:423-499) on a PIL frame, and save_network -> create_network_from_config_file
+    (network.py:29-63, 592-632): identical keypoints after the round trip; 640x480 'shrink-and-crop' to 400x400."""
+    from PIL import Image
+    from conftest import panda_config
+    from dream_b200 import network
+    cfg = panda_config("vgg")
+    cfg["training"]["config"]["net_input_resolution"] = [200, 200]
+    net = network.create_network_from_config_data(cfg)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=8, out_gain=13.0, mode="default")
+    net.model.load_state_dict(sd)
+    net.enable_evaluation()
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 255, size=(480, 640, 3), dtype=np.uint8), "RGB")
+    res = net.keypoints_from_image(img, debug=True)
+    assert res["detected_keypoints"].shape == (7, 2)
+    assert res["image_rgb_net_input"].size == (200, 200)
+    assert tuple(res["belief_maps"].shape) == (7, 50, 50)
+    # the same frame through the oracle: preprocess -> normalise -> reference forward -> reference peak logic
+    arr = np.asarray(res["image_rgb_net_input"].convert("RGB"), dtype=np.float32) / 255.0
+    x = torch.from_numpy(((arr - 0.5) / 0.5).transpose(2, 0, 1)[None].copy())
+    ref_maps = ref_models.vgg_forward(sd, x).detach().numpy()[0]
+    assert np.abs(res["belief_maps"].cpu().numpy() - ref_maps).max() <= BELIEF_TOL * max(1.0, np.abs(ref_maps).max())
+    ref_k = np.array(ref_peaks.select_keypoints(
+        ref_peaks.peaks_from_belief_maps(res["belief_maps"].cpu().numpy(), 0.4395)), dtype=np.float32)
+    assert np.array_equal(ref_k, res["detected_keypoints_net_output"].astype(np.float32))
+    # checkpoint round trip
+    net.save_network(str(tmp_path), "ckpt", overwrite=True)
+    assert (tmp_path / "ckpt.pth").exists() and (tmp_path / "ckpt.yaml").exists()
+    assert all(k.startswith("module.") for k in torch.load(tmp_path / "ckpt.pth").keys())
+    net2 = network.create_network_from_config_file(str(tmp_path / "ckpt.yaml"), str(tmp_path / "ckpt.pth"))
+    net2.enable_evaluation()
+    res2 = net2.keypoints_from_image(img)
+    assert np.array_equal(res["detected_keypoints"], res2["detected_keypoints"])
