@@ -44,6 +44,7 @@ struct WgradParams {
   int stages;
   int a_stride;             // 1: conv (dY on X's grid); 2: ConvTranspose stride 2 (dY on the 2x finer grid)
   int shift_a;              // tap offset applied to the dY coordinates (ConvTranspose) instead of X's
+  int b_stride;             // 2: stride-2 convolution (X on the 2x finer grid, tiles run over dY's grid)
 };
 
 constexpr int kWgThreads = 192;
@@ -112,7 +113,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const uint32_t sa = smem_base + stage * kStageBytes;
         mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
         const int ax = x0 * p.a_stride + (p.shift_a ? p.dx[tap] : 0), ay = y0 * p.a_stride + (p.shift_a ? p.dy[tap] : 0);
-        const int bx = x0 + (p.shift_a ? 0 : p.dx[tap]), by = y0 + (p.shift_a ? 0 : p.dy[tap]);
+        const int bx = x0 * p.b_stride + (p.shift_a ? 0 : p.dx[tap]), by = y0 * p.b_stride + (p.shift_a ? 0 : p.dy[tap]);
 #pragma unroll
         for (int m = 0; m < 2; ++m)
           tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, ax, ay, b);
@@ -368,6 +369,164 @@ __global__ void bias_grad_kernel(const __half* __restrict__ dy, float* __restric
   }
 }
 
+// ---- BatchNorm2d in training mode (torchvision ResNet trunk + decoder BNs, models.py:22-32,46-76) ----
+// per-channel sum and sum of squares of z [rows, C] fp16 (fp32 accumulation, fp32 atomics; caller zeroes outputs)
+__global__ void bn_stats_kernel(const __half* __restrict__ z, float* __restrict__ sum, float* __restrict__ sumsq,
+                                long long rows, int C) {
+  const int cg = blockIdx.y;
+  const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+  const int c = cg * 64 + tc * 2;
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long r = (long long)blockIdx.x * 8 + tr; r < rows; r += (long long)gridDim.x * 8) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(z + (size_t)r * C + c));
+    a0 += f.x; a1 += f.y; q0 += f.x * f.x; q1 += f.y * f.y;
+  }
+  __shared__ float sh[2][8][64];
+  sh[0][tr][tc * 2] = a0; sh[0][tr][tc * 2 + 1] = a1;
+  sh[1][tr][tc * 2] = q0; sh[1][tr][tc * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += sh[which][i][ch];
+    atomicAdd((which ? sumsq : sum) + cg * 64 + ch, v);
+  }
+}
+
+// y = relu?( z * scale[c] + shift[c] (+ residual) ), fp16 in / out, 8 channels per thread
+__global__ void bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const uint4* __restrict__ residual,
+                                uint4* __restrict__ y, long long n8, int C8, int relu) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8) * 8;
+    const uint4 v = __ldg(z + idx);
+    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+    uint4 rv = make_uint4(0, 0, 0, 0);
+    if (residual != nullptr) rv = __ldg(residual + idx);
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(vh[j]);
+      const float2 r = __half22float2(rh[j]);
+      float a = f.x * __ldg(scale + c + 2 * j) + __ldg(shift + c + 2 * j) + r.x;
+      float b = f.y * __ldg(scale + c + 2 * j + 1) + __ldg(shift + c + 2 * j + 1) + r.y;
+      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      oh[j] = __floats2half2_rn(a, b);
+    }
+    y[idx] = o;
+  }
+}
+
+// BN backward reductions: sum_dy[c] += sum dy, sum_dyz[c] += sum dy * z   (dy already ReLU-masked)
+__global__ void bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ z,
+                                     float* __restrict__ sum_dy, float* __restrict__ sum_dyz, long long rows, int C) {
+  const int cg = blockIdx.y;
+  const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+  const int c = cg * 64 + tc * 2;
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long r = (long long)blockIdx.x * 8 + tr; r < rows; r += (long long)gridDim.x * 8) {
+    const float2 g = __half22float2(*reinterpret_cast<const __half2*>(dy + (size_t)r * C + c));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(z + (size_t)r * C + c));
+    a0 += g.x; a1 += g.y; q0 += g.x * f.x; q1 += g.y * f.y;
+  }
+  __shared__ float sh[2][8][64];
+  sh[0][tr][tc * 2] = a0; sh[0][tr][tc * 2 + 1] = a1;
+  sh[1][tr][tc * 2] = q0; sh[1][tr][tc * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += sh[which][i][ch];
+    atomicAdd((which ? sum_dyz : sum_dy) + cg * 64 + ch, v);
+  }
+}
+
+// dz = a[c] * dy + b[c] * z + c0[c]   (BN backward, coefficients precomputed per channel), in place on dy
+__global__ void bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ z, const float* __restrict__ a,
+                                    const float* __restrict__ b, const float* __restrict__ c0, long long n8, int C8) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8) * 8;
+    uint4 g = dy[idx];
+    const uint4 v = __ldg(z + idx);
+    __half2* gh = reinterpret_cast<__half2*>(&g);
+    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 gf = __half22float2(gh[j]);
+      const float2 zf = __half22float2(vh[j]);
+      const int c0i = c + 2 * j;
+      gh[j] = __floats2half2_rn(__ldg(a + c0i) * gf.x + __ldg(b + c0i) * zf.x + __ldg(c0 + c0i),
+                                __ldg(a + c0i + 1) * gf.y + __ldg(b + c0i + 1) * zf.y + __ldg(c0 + c0i + 1));
+    }
+    dy[idx] = g;
+  }
+}
+
+// 3x3 / stride 2 / pad 1 max-pool backward (resnet stem, models.py:27): every input pixel gathers from the <= 4
+// windows that contain it; a window's gradient goes to its first maximum in (row, col) scan order, like ATen.
+__global__ void maxpool3_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                    int B, int H, int W, int C8, int Ho, int Wo) {
+  const long long total = (long long)B * H * W * C8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    long long pix = idx / C8;
+    const int ix = (int)(pix % W);
+    pix /= W;
+    const int iy = (int)(pix % H);
+    const int b = (int)(pix / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint4 mine = __ldg(x + idx);
+    const __half* mh = reinterpret_cast<const __half*>(&mine);
+    // windows (oy, ox) with 2*oy-1 <= iy <= 2*oy+1
+    for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= Ho) continue;
+      for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= Wo) continue;
+        const uint4 g = __ldg(dy + ((size_t)((size_t)b * Ho + oy) * Wo + ox) * C8 + c);
+        const __half* gh = reinterpret_cast<const __half*>(&g);
+        // position of (iy, ix) in the window's scan order
+        const int my_r = iy - (2 * oy - 1), my_c = ix - (2 * ox - 1);
+        bool win[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = true;
+        for (int r = 0; r < 3; ++r) {
+          const int yy = 2 * oy - 1 + r;
+          if (yy < 0 || yy >= H) continue;
+          for (int q = 0; q < 3; ++q) {
+            const int xx = 2 * ox - 1 + q;
+            if (xx < 0 || xx >= W) continue;
+            if (r == my_r && q == my_c) continue;
+            const uint4 v = __ldg(x + ((size_t)((size_t)b * H + yy) * W + xx) * C8 + c);
+            const __half* vh = reinterpret_cast<const __half*>(&v);
+            const bool before = (r < my_r) || (r == my_r && q < my_c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float o = __half2float(vh[j]), m = __half2float(mh[j]);
+              // an earlier element wins ties (>=), a later one only if strictly greater
+              if (before ? (o >= m) : (o > m)) win[j] = false;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (win[j]) acc[j] += __half2float(gh[j]);
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    dx[idx] = o;
+  }
+}
+
 static int grid_cap(long long work, int threads) {
   long long blocks = (work + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 16;
@@ -380,8 +539,9 @@ static int grid_cap(long long work, int threads) {
 
 using namespace db200;
 
-static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, int W, int Hd, int Wd, int a_stride,
-                      int shift_a, int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+// H, W: the grid the pixel tiles run over (the coarser of the two operands); Hd x Wd: dY extent; Hx x Wx: X extent
+static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, int W, int Hd, int Wd, int Hx, int Wx,
+                      int a_stride, int b_stride, int shift_a, int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
                       cudaStream_t stream) {
   DB_REQUIRE(dy && x && dw && tap_dy && tap_dx, "wgrad: null pointer");
   DB_REQUIRE(Cout_pad % 64 == 0 && Cin_pad % 64 == 0, "wgrad: channel counts must be multiples of 64 (%d, %d)",
@@ -398,6 +558,7 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
   memcpy(p.dy, tap_dy, taps);
   memcpy(p.dx, tap_dx, taps);
   p.a_stride = a_stride;
+  p.b_stride = b_stride;
   p.shift_a = shift_a;
   const int block_n = Cin_pad % 128 == 0 ? 128 : 64;
   p.co_tiles = (Cout_pad + 127) / 128;   // a half-empty last tile is zero-filled by TMA
@@ -422,10 +583,11 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
     if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad dY")) return -1;
   }
   {
-    const uint32_t box[4] = {64, kWgTw, kWgTh, 1};
-    const uint32_t es[4] = {1, 1, 1, 1};
-    uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
+    const uint32_t s = (uint32_t)b_stride;
+    const uint32_t box[4] = {64, kWgTw * s, kWgTh * s, 1};
+    const uint32_t es[4] = {1, s, s, 1};
+    uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)Wx, (uint64_t)Hx, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)Wx * Cin_pad * 2, (uint64_t)Hx * Wx * Cin_pad * 2};
     if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad X")) return -1;
   }
   if (block_n == 128) return launch_wgrad<128>(tmDY, tmX, p, stream);
@@ -434,13 +596,23 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
 
 extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
                                int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
-  return wgrad_impl(dy, x, dw, B, H, W, H, W, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx, (cudaStream_t)stream_v);
+  return wgrad_impl(dy, x, dw, B, H, W, H, W, H, W, 1, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
+                    (cudaStream_t)stream_v);
 }
 
 extern "C" int dreamb200_wgrad_deconv(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
                                       int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
                                       void* stream_v) {
-  return wgrad_impl(dy, x, dw, B, H, W, 2 * H, 2 * W, 2, 1, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
+  return wgrad_impl(dy, x, dw, B, H, W, 2 * H, 2 * W, H, W, 2, 1, 1, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
+                    (cudaStream_t)stream_v);
+}
+
+// weight gradient of a stride-2 convolution: dy [B,Ho,Wo,Cout_pad], x [B,Hx,Wx,Cin_pad] with Ho=(Hx-1)/2+1:
+// dW[tap][co][ci] += sum_p dY[p][co] * X[2p + tap][ci]
+extern "C" int dreamb200_wgrad_strided(const void* dy, const void* x, float* dw, int B, int Ho, int Wo, int Hx, int Wx,
+                                       int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                                       void* stream_v) {
+  return wgrad_impl(dy, x, dw, B, Ho, Wo, Ho, Wo, Hx, Wx, 1, 2, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
                     (cudaStream_t)stream_v);
 }
 
@@ -502,6 +674,68 @@ extern "C" int dreamb200_bias_grad(const void* dy, float* db, long long rows, in
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)(C / 64));
   bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(dy), db, rows, C);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static dim3 reduce_grid(long long rows, int C) {
+  long long bx = (rows + 8 * 64 - 1) / (8 * 64);
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)(C / 64));
+}
+
+extern "C" int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, void* stream) {
+  DB_REQUIRE(z && sum && sumsq && rows > 0 && C % 64 == 0, "bn_stats: bad arguments");
+  bn_stats_kernel<<<reduce_grid(rows, C), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(z), sum,
+                                                                          sumsq, rows, C);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_bn_apply_f16(const void* z, const float* scale, const float* shift, const void* residual,
+                                      void* y, long long rows, int C, int relu, void* stream) {
+  DB_REQUIRE(z && scale && shift && y && rows > 0 && C % 8 == 0, "bn_apply: bad arguments");
+  const long long n8 = rows * C / 8;
+  bn_apply_kernel<<<grid_cap(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
+      reinterpret_cast<uint4*>(y), n8, C / 8, relu);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_bn_bwd_reduce_f16(const void* dy, const void* z, float* sum_dy, float* sum_dyz, long long rows,
+                                           int C, void* stream) {
+  DB_REQUIRE(dy && z && sum_dy && sum_dyz && rows > 0 && C % 64 == 0, "bn_bwd_reduce: bad arguments");
+  bn_bwd_reduce_kernel<<<reduce_grid(rows, C), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(z), sum_dy, sum_dyz, rows, C);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_bn_bwd_apply_f16(void* dy, const void* z, const float* a, const float* b, const float* c0,
+                                          long long rows, int C, void* stream) {
+  DB_REQUIRE(dy && z && a && b && c0 && rows > 0 && C % 8 == 0, "bn_bwd_apply: bad arguments");
+  const long long n8 = rows * C / 8;
+  bn_bwd_apply_kernel<<<grid_cap(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<uint4*>(dy), reinterpret_cast<const uint4*>(z), a, b, c0, n8, C / 8);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_maxpool3_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C,
+                                           void* stream) {
+  DB_REQUIRE(x && dy && dx && C % 8 == 0, "maxpool3_bwd: bad arguments");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)B * H * W * (C / 8);
+  maxpool3_bwd_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), B, H, W,
+      C / 8, Ho, Wo);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

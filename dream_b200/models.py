@@ -456,9 +456,9 @@ class ResnetSimple(_PlanModule):
 
     def forward(self, x):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "ResnetSimple training (BatchNorm batch statistics + backward) is not built yet in "
-                "dream_b200; inference (eval mode / torch.no_grad()) is supported.")
+            from .autograd_resnet import resnet_train_forward
+            return [resnet_train_forward(self, x)]
+        # (train() mode under torch.no_grad(), e.g. the constructor's shape probe, uses the running statistics)
         return [self.belief_maps(x)]
 
 

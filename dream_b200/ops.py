@@ -300,3 +300,60 @@ def bias_grad(dy):
     db = torch.zeros((Cc,), dtype=torch.float32, device=dy.device)
     check(lib().dreamb200_bias_grad(_ptr(dy), _ptr(db), dy.numel() // Cc, Cc, _stream()), "dreamb200_bias_grad")
     return db
+
+
+# ----------------------------------------------------------------------------------------------
+# BatchNorm (training mode) and strided backward wrappers
+# ----------------------------------------------------------------------------------------------
+def wgrad_strided(dy, x, taps):
+    """Weight gradient of a stride-2 conv: dW[tap][co][ci] = sum_p dy[p][co] * x[2p + tap][ci]."""
+    B, Ho, Wo, Co = dy.shape
+    _, Hx, Wx, Ci = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and dy.dtype == torch.float16 and x.dtype == torch.float16
+    dw = torch.zeros((len(taps), Co, Ci), dtype=torch.float32, device=dy.device)
+    tdy = (C.c_int8 * len(taps))(*[t[0] for t in taps])
+    tdx = (C.c_int8 * len(taps))(*[t[1] for t in taps])
+    check(lib().dreamb200_wgrad_strided(_ptr(dy), _ptr(x), _ptr(dw), B, Ho, Wo, Hx, Wx, Co, Ci, len(taps),
+                                        C.cast(tdy, C.c_void_p), C.cast(tdx, C.c_void_p), _stream()),
+          "dreamb200_wgrad_strided")
+    return dw
+
+
+def bn_stats(z):
+    """Per-channel (sum, sum of squares) of an fp16 NHWC tensor, fp32 [C] each."""
+    Cc = z.shape[-1]
+    s = torch.zeros((2, Cc), dtype=torch.float32, device=z.device)
+    check(lib().dreamb200_bn_stats_f16(_ptr(z), _ptr(s[0]), _ptr(s[1]), z.numel() // Cc, Cc, _stream()),
+          "dreamb200_bn_stats_f16")
+    return s[0], s[1]
+
+
+def bn_apply(z, scale, shift, residual=None, relu=False):
+    y = torch.empty_like(z)
+    Cc = z.shape[-1]
+    check(lib().dreamb200_bn_apply_f16(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y),
+                                       z.numel() // Cc, Cc, 1 if relu else 0, _stream()), "dreamb200_bn_apply_f16")
+    return y
+
+
+def bn_bwd_reduce(dy, z):
+    Cc = z.shape[-1]
+    s = torch.zeros((2, Cc), dtype=torch.float32, device=z.device)
+    check(lib().dreamb200_bn_bwd_reduce_f16(_ptr(dy), _ptr(z), _ptr(s[0]), _ptr(s[1]), z.numel() // Cc, Cc,
+                                            _stream()), "dreamb200_bn_bwd_reduce_f16")
+    return s[0], s[1]
+
+
+def bn_bwd_apply_(dy, z, a, b, c0):
+    Cc = z.shape[-1]
+    check(lib().dreamb200_bn_bwd_apply_f16(_ptr(dy), _ptr(z), _ptr(a), _ptr(b), _ptr(c0), z.numel() // Cc, Cc,
+                                           _stream()), "dreamb200_bn_bwd_apply_f16")
+    return dy
+
+
+def maxpool3_bwd(x, dy):
+    B, H, W_, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(lib().dreamb200_maxpool3_bwd_nhwc(_ptr(x), _ptr(dy), _ptr(dx), B, H, W_, Cc, _stream()),
+          "dreamb200_maxpool3_bwd_nhwc")
+    return dx

@@ -109,6 +109,24 @@ int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int 
    dW[tap][co][ci] += sum_pixels dY[2p + tap][co] * X[p][ci]; x [B,H,W,Cin_pad], dy [B,2H,2W,Cout_pad] */
 int dreamb200_wgrad_deconv(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
                            int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream);
+/* weight gradient of a stride-2 convolution: dy [B,Ho,Wo,Cout_pad], x [B,Hx,Wx,Cin_pad]:
+   dW[tap][co][ci] += sum_pixels dY[p][co] * X[2p + tap][ci] */
+int dreamb200_wgrad_strided(const void* dy, const void* x, float* dw, int B, int Ho, int Wo, int Hx, int Wx,
+                            int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
+                            void* stream);
+/* nn.BatchNorm2d in training mode (ResNet trunk / decoder, models.py:22-32,46-76), z fp16 [rows, C]:
+   bn_stats: sum[c] += sum_rows z, sumsq[c] += sum_rows z^2 (caller zeroes; C % 64 == 0);
+   bn_apply: y = relu?(z*scale[c] + shift[c] (+ residual)) fp16;
+   bn_bwd_reduce: sum_dy[c] += sum dy, sum_dyz[c] += sum dy*z;  bn_bwd_apply: dy = a[c]*dy + b[c]*z + c0[c] in place */
+int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, void* stream);
+int dreamb200_bn_apply_f16(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                           long long rows, int C, int relu, void* stream);
+int dreamb200_bn_bwd_reduce_f16(const void* dy, const void* z, float* sum_dy, float* sum_dyz, long long rows, int C,
+                                void* stream);
+int dreamb200_bn_bwd_apply_f16(void* dy, const void* z, const float* a, const float* b, const float* c0,
+                               long long rows, int C, void* stream);
+/* autograd of MaxPool2d(3, stride 2, padding 1) (resnet stem): x [B,H,W,C], dy [B,(H-1)/2+1,(W-1)/2+1,C] */
+int dreamb200_maxpool3_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 /* dy = dy * (*scale) * (y > 0): autograd of nn.ReLU given its output, fused with the power-of-two
    re-scaling that keeps fp16 gradients in range; y and/or scale may be NULL */
 int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream);

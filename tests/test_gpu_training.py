@@ -196,6 +196,49 @@ def test_vgg_f_training_gradients_track_oracle(built_lib):
             assert _rel(got, ref) <= 1e-2, (name, _rel(got, ref))
 
 
+@pytest.mark.parametrize("full", [False, True])
+def test_resnet_training_matches_oracle(full, built_lib):
+    """ResnetSimple in training mode (BatchNorm batch statistics, residual blocks, stride-2 convs, 7x7 stem,
+    ConvTranspose decoder): loss, running statistics and every parameter gradient vs the oracle's autograd."""
+    from dream_b200 import models
+    shapes = ref_models.resnet_state_shapes(7, full=full, prefix="")
+    sd = ref_models.synth_state_dict(shapes, seed=3, out_gain=0.04, mode="he")
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand((2, 3, 96, 80), generator=gen) * 2 - 1
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not ("running" in k) else v.clone())
+           for k, v in sd.items()}
+    y = ref_models.resnet_forward(osd, x, full=full, training=True, prefix="")
+    target = torch.rand(y.shape, generator=gen)
+    ref_loss = torch.nn.functional.mse_loss(y, target)
+    ref_loss.backward()
+
+    net = models.ResnetSimple(7, full=full)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    out = net(x.cuda())[0]
+    assert tuple(out.shape) == tuple(y.shape)
+    loss = torch.nn.MSELoss()(out, target.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * ref_loss.item(), (loss.item(), ref_loss.item())
+    # running statistics were updated like nn.BatchNorm2d (momentum 0.1, unbiased variance)
+    for k in ("bn1", "layer3.5.bn2", "upsample.1"):
+        rm, rv = dict(net.named_buffers())[k + ".running_mean"].cpu(), dict(net.named_buffers())[k + ".running_var"].cpu()
+        assert _rel(rm, osd[k + ".running_mean"]) <= 5e-3, (k, _rel(rm, osd[k + ".running_mean"]))
+        assert _rel(rv, osd[k + ".running_var"]) <= 5e-3, (k, _rel(rv, osd[k + ".running_var"]))
+    assert int(dict(net.named_buffers())["bn1.num_batches_tracked"]) == 1
+    worst_cos = 1.0
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        got, ref = p.grad.cpu(), osd[name].grad
+        c = _cos(got, ref)
+        worst_cos = min(worst_cos, c)
+        assert c >= 0.97, (name, c)
+        assert abs(float(got.norm() / ref.norm().clamp_min(1e-30)) - 1.0) <= 0.06, (name, float(got.norm() / ref.norm()))
+    print("resnet full=%s worst gradient cosine %.5f" % (full, worst_cos))
+    head = "upsample2.3" if full else "upsample.12"
+    assert _rel(dict(net.named_parameters())[head + ".weight"].grad.cpu(), osd[head + ".weight"].grad) <= 1e-2
+
+
 def test_training_steps_track_oracle_loss_curve(built_lib):
     """A few SGD steps through DreamNetwork.train vs the same steps on the oracle (same seed/weights)."""
     from conftest import panda_config

@@ -25,3 +25,4 @@ for name, p in net.named_parameters():
     rel = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
     cos = float((got * ref).sum() / (got.norm() * ref.norm()).clamp_min(1e-30))
     print("%-28s rel %.4f cos %.6f |ref| %.3g |got| %.3g" % (name, rel, cos, ref.norm().item(), got.norm().item()))
+
