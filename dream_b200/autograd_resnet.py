@@ -24,6 +24,10 @@ from . import models, ops
 BN_MOMENTUM = 0.1
 EPS = 1e-5
 
+# Test hook: when a list, backward appends per conv+BN unit a dict with the unit, the incoming dL/dy (fp16 clone,
+# before the ReLU mask), the scale it carries, and the produced dL/dx (fp16 clone) with its scale.
+DEBUG_CAPTURE = None
+
 
 def _pad_vec(v, n):
     out = torch.zeros((n,), dtype=torch.float32, device=v.device)
@@ -166,6 +170,10 @@ class _ResnetTrainFn(torch.autograd.Function):
                 acc(xin, ops.maxpool3_bwd(xin, G.pop(id(yout))))
                 continue
             g = G.pop(id(u.y))
+            cap = None
+            if DEBUG_CAPTURE is not None:
+                cap = {"unit": u, "g_in": g.clone(), "cum_in": cum.clone()}
+                DEBUG_CAPTURE.append(cap)
             if u.block_end:
                 # single live gradient here: refresh the loss scale (power of two, computed on the device)
                 f = torch.exp2(torch.floor(torch.log2(256.0 / ops.absmax(g).clamp_min(1e-30)))).clamp(2.0 ** -12, 2.0 ** 12)
@@ -202,11 +210,16 @@ class _ResnetTrainFn(torch.autograd.Function):
                 grads[u.conv_key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(ci, co, 4, 4).contiguous()
                 wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=u.x.shape[3])
                 B, H, W, _ = u.x.shape
-                acc(u.x, ops.conv_taps(g, wd, None, taps, H, W, stride=2))
+                dx = ops.conv_taps(g, wd, None, taps, H, W, stride=2)
+                if cap is not None:
+                    cap["dx"], cap["cum_out"] = dx.clone(), cum.clone()
+                acc(u.x, dx)
             elif u.kind == "first":
                 co = node.weight.shape[0]
                 dw = ops.wgrad(g, u.x, [(0, 0)])[0, :co, :147]                        # [co, (r,s,c)]
                 grads[u.conv_key + ".weight"] = (dw * inv).view(co, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+                if cap is not None:
+                    cap["cum_out"] = cum.clone()
             else:
                 co, ci, ksz = node.weight.shape[0], node.weight.shape[1], node.weight.shape[2]
                 pad = ksz // 2
@@ -223,6 +236,8 @@ class _ResnetTrainFn(torch.autograd.Function):
                     dw = ops.wgrad_strided(g, u.x, taps)[:, :co, :ci]
                     dx = _dgrad_stride2(node.weight.detach(), g, u.x.shape)
                 grads[u.conv_key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(co, ci, ksz, ksz).contiguous()
+                if cap is not None:
+                    cap["dx"], cap["cum_out"] = dx.clone(), cum.clone()
                 acc(u.x, dx)
         ctx.tape = None
         return (None, None) + tuple(grads.get(n) for n in ctx.param_names)
