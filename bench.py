@@ -36,6 +36,7 @@ WORKLOADS = {
     "resnet_h_infer": ({"type": "resnet"}, 64, (400, 400), 82.870, "infer"),
     "resnet_f_infer": ({"type": "resnet", "full_decoder": True}, 16, (480, 640), 315.546, "infer"),
     "vgg_q_train": ({"type": "vgg"}, 128, (400, 400), 424.79, "train"),
+    "resnet_h_train": ({"type": "resnet"}, 32, (400, 400), 3 * 82.870, "train"),
 }
 
 
@@ -344,7 +345,8 @@ def main():
             "config": {"workload": {"vgg_q_infer": "DREAM-vgg-Q inference (forward + peak extraction)",
                                     "resnet_h_infer": "DREAM-resnet-H inference (forward + peak extraction)",
                                     "resnet_f_infer": "DREAM-resnet-F inference (forward + peak extraction)",
-                                    "vgg_q_train": "DREAM-vgg-Q training step (fwd + MSE + bwd + allreduce + Adam)"}[
+                                    "vgg_q_train": "DREAM-vgg-Q training step (fwd + MSE + bwd + allreduce + Adam)",
+                                    "resnet_h_train": "DREAM-resnet-H training step (fwd + MSE + bwd + allreduce + Adam)"}[
                            args.workload] + ", batch %d/GPU, %dx%d, 7 keypoints" % (B, W, H),
                        "parallelism": "frames sharded over %d GPU(s), no collective" % world,
                        "l2": "inputs rotate over 2 batches (157 MB > 126 MB L2); ~10 GB of activations stream per step"},

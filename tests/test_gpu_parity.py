@@ -344,7 +344,7 @@ def test_facade_single_image_and_checkpoint_round_trip(tmp_path, built_lib):
     res = net.keypoints_from_image(img, debug=True)
     assert res["detected_keypoints"].shape == (7, 2)
     assert res["image_rgb_net_input"].size == (200, 200)
-    assert tuple(res["belief_maps"].shape) == (7, 50, 50)
+    assert tuple(res["belief_maps"].shape) == (7, 48, 48)      # 200 -> 100 -> 50 -> 25 -> 12 (floor) -> x4
     # the same frame through the oracle: preprocess -> normalise -> reference forward -> reference peak logic
     arr = np.asarray(res["image_rgb_net_input"].convert("RGB"), dtype=np.float32) / 255.0
     x = torch.from_numpy(((arr - 0.5) / 0.5).transpose(2, 0, 1)[None].copy())
