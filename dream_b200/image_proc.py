@@ -99,9 +99,8 @@ def select_keypoints_device(table, next_best_score, sentinel=-999.999):
     gap = s[:, 2].float() - s[:, 3].float()
     take = (cnt == 1) | ((cnt > 1) & (gap >= torch.tensor(next_best_score, dtype=torch.float32,
                                                           device=gap.device)))
-    out = torch.full((table.n_maps, 2), sentinel, dtype=torch.float64, device=cnt.device)
-    out[take] = s[take, :2]
-    return out
+    # torch.where, not boolean-mask assignment: no data-dependent shape, hence no hidden host sync
+    return torch.where(take.unsqueeze(1), s[:, :2], torch.full_like(s[:, :2], sentinel))
 
 
 def create_belief_map(image_resolution, pointsBelief, sigma=2):

@@ -341,20 +341,25 @@ class DreamNetwork:
         if output_heads == ["belief_maps", "keypoints"]:
             return self.model(network_input)
         if output_heads == ["belief_maps"]:
-            belief_maps_batch = self.model(network_input)[-1]
-            tw, th = self.trained_net_output_resolution()
-            offset = 0.0 if (tw >= 400 and th >= 400) else 0.4395     # network.py:534-538
-            B, K = belief_maps_batch.shape[0], belief_maps_batch.shape[1]
-            table = image_proc.find_peaks_device(belief_maps_batch.detach(), offset)
-            if self.use_belief_peak_scores:
-                kps = image_proc.select_keypoints_device(table, self.belief_peak_next_best_score)
-            else:
-                one = table.counts == 1
-                kps = torch.full((table.n_maps, 2), -999.999, dtype=torch.float64, device=table.counts.device)
-                kps[one] = table.summary[one, :2]
-            detected_kp_projs_batch = kps.view(B, K, 2).cpu().float()
-            return [belief_maps_batch, detected_kp_projs_batch]
+            belief_maps_batch, kps_dev = self.inference_device(network_input)
+            return [belief_maps_batch, kps_dev.cpu().float()]          # the ONE device->host copy of the batch
         assert False, "Could not determine how to conduct inference on this network."
+
+    def inference_device(self, network_input):
+        """`inference` without the final host copy: (belief maps [B,K,h,w] cuda, keypoints [B,K,2] float64 cuda).
+        Nothing here synchronises with the host, so callers can queue the next batch before reading this one
+        (dream_b200.pipeline.inference_stream does)."""
+        belief_maps_batch = self.model(network_input)[-1]
+        tw, th = self.trained_net_output_resolution()
+        offset = 0.0 if (tw >= 400 and th >= 400) else 0.4395     # network.py:534-538
+        B, K = belief_maps_batch.shape[0], belief_maps_batch.shape[1]
+        table = image_proc.find_peaks_device(belief_maps_batch.detach(), offset)
+        if self.use_belief_peak_scores:
+            kps = image_proc.select_keypoints_device(table, self.belief_peak_next_best_score)
+        else:
+            one = (table.counts == 1).unsqueeze(1)
+            kps = torch.where(one, table.summary[:, :2], torch.full_like(table.summary[:, :2], -999.999))
+        return belief_maps_batch, kps.view(B, K, 2)
 
     # ------------------------------------------------------------------------------------------
     def save_network_config(self, config_file_path, overwrite=False):

@@ -51,10 +51,29 @@ class DevicePrefetcher:
 
 
 def inference_stream(network, host_batches):
-    """Yields `network.inference(x)` ([belief_maps cuda, keypoints cpu]) for every host batch."""
+    """Yields `[belief_maps (cuda), keypoints (cpu fp32 [B,K,2])]` -- what `network.inference(x)` returns -- for
+    every host batch.  Software-pipelined by one batch: the kernels of batch i+1 are queued before the host waits
+    for the keypoints of batch i, so neither the PCIe copy nor the launch overhead sits on the critical path."""
+    if network.network_config["architecture"]["output_heads"] != ["belief_maps"]:
+        with torch.no_grad():
+            for x in DevicePrefetcher(host_batches, network.device):
+                yield network.inference(x)
+        return
+    pending = None
     with torch.no_grad():
         for x in DevicePrefetcher(host_batches, network.device):
-            yield network.inference(x)
+            belief, kps_dev = network.inference_device(x)
+            kps_host = torch.empty(kps_dev.shape, dtype=torch.float32).pin_memory()
+            kps_host.copy_(kps_dev, non_blocking=True)          # float64 -> float32 conversion happens on the device
+            done = torch.cuda.Event()
+            done.record()
+            if pending is not None:
+                pending[2].synchronize()
+                yield [pending[0], pending[1]]
+            pending = (belief, kps_host, done)
+        if pending is not None:
+            pending[2].synchronize()
+            yield [pending[0], pending[1]]
 
 
 def train_stream(network, host_batches):

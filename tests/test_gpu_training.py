@@ -237,8 +237,7 @@ def test_resnet_training_matches_oracle(full, built_lib):
     for name, p in params.items():
         assert p.grad is not None, name
         got, ref = p.grad.cpu(), osd[name].grad
-        if name.endswith(".bias") and (name[:-4] + "weight") in params and name.startswith("upsample") \
-                and not name.startswith(("upsample.12", "upsample2.3")):
+        if name in ("upsample.0.bias", "upsample.3.bias", "upsample.6.bias", "upsample.9.bias", "upsample2.0.bias"):
             # a conv bias in front of a batch-statistics BatchNorm has an exactly zero gradient; both sides hold noise
             assert float(got.norm()) <= 1e-3 * float(params[name[:-4] + "weight"].grad.norm()), name
             continue
