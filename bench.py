@@ -196,7 +196,9 @@ def main():
 
     arch, b_default, (H, W), gflop_img, mode = WORKLOADS[args.workload]
     B = args.batch or b_default
-    net = network.create_network_from_config_data(make_config(arch, (H, W)))
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # the facade prints its banner like the reference; stdout = the JSON line
+        net = network.create_network_from_config_data(make_config(arch, (H, W)))
     model = net.model.module
     if mode == "train":
         net.enable_training()
