@@ -25,7 +25,23 @@ struct ConvParams {
   int stages;
   int pool;         // fused 2x2/s2 max pool of the output tile (tw, th even): pooled tile -> tmP
   int store_full;   // also store the un-pooled tile through tmC
+  // division-free tile decode: q = (x * magic) >> 40 is exact for x < 2^24, divisor < 2^16 (host: 2^40/d + 1)
+  unsigned long long mg_n, mg_x, mg_y;
 };
+
+__host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
+__device__ __forceinline__ int fast_div(int x, unsigned long long magic) {
+  return (int)(((unsigned long long)(unsigned)x * magic) >> 40);
+}
+// tile index -> (output-channel tile n, patch column tx, patch row ty, image b); n varies fastest
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& n, int& tx, int& ty, int& b) {
+  int t = fast_div(tile, p.mg_n);
+  n = tile - t * p.n_tiles;
+  int t2 = fast_div(t, p.mg_x);
+  tx = t - t2 * p.tiles_x;
+  b = fast_div(t2, p.mg_y);
+  ty = t2 - b * p.tiles_y;
+}
 
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 rows x 64 fp16
@@ -160,7 +176,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
         hv[i] = *reinterpret_cast<uint32_t*>(&m);
       }
       if ((lane & 1) == 0 && (lane & p.tw) == 0) {
-        const int ly = row / p.tw, lx = row - ly * p.tw;
+        const int sh = p.tw == 8 ? 3 : 4;                       // tw is 8 or 16 here
+        const int ly = row >> sh, lx = row & (p.tw - 1);
         const int pr = (ly >> 1) * (p.tw >> 1) + (lx >> 1);
 #pragma unroll
         for (int j = 0; j < 8 / SPLIT; ++j) {

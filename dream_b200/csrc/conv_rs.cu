@@ -118,11 +118,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as_ = 0, bs_ = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int n = tile % p.n_tiles;
-        int t = tile / p.n_tiles;
-        int tx = t % p.tiles_x; t /= p.tiles_x;
-        int ty = t % p.tiles_y;
-        int b = t / p.tiles_y;
+        int n, tx, ty, b;
+        decode_tile(p, tile, n, tx, ty, b);
         const int x0 = tx * kRsTw, y0 = ty * kRsTh * SUBTILES;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int s = 0; s < 3; ++s) {
@@ -215,11 +212,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t accph = 0;
     uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int n = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
-      int tx = t % p.tiles_x; t /= p.tiles_x;
-      int ty = t % p.tiles_y;
-      int b = t / p.tiles_y;
+      int n, tx, ty, b;
+      decode_tile(p, tile, n, tx, ty, b);
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
 #pragma unroll 1
@@ -256,6 +250,12 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.n_tiles = d->Cout_pad / BLOCK_N;
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * d->B;
+  DB_REQUIRE((long long)p.tiles_x * p.tiles_y * p.n_tiles * d->B < (1ll << 24) && p.tiles_x < 65536 &&
+                 p.tiles_y < 65536 && p.n_tiles < 65536,
+             "conv: too many tiles for one launch (%d x %d x %d x %d)", p.tiles_x, p.tiles_y, p.n_tiles, d->B);
+  p.mg_n = div_magic(p.n_tiles);
+  p.mg_x = div_magic(p.tiles_x);
+  p.mg_y = div_magic(p.tiles_y);
   p.in_stride = 1;
   p.taps = 9;
   p.kchunks = d->Cin / 64;

@@ -97,12 +97,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int n = tile % p.n_tiles;
-        int t = tile / p.n_tiles;
-        int tx = t % p.tiles_x;
-        t /= p.tiles_x;
-        int ty = t % p.tiles_y;
-        int b = t / p.tiles_y;
+        int n, tx, ty, b;
+        decode_tile(p, tile, n, tx, ty, b);
         const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int xi = x0 + p.dx[tap], yi = y0 + p.dy[tap];
@@ -160,12 +156,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int n = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
-      int tx = t % p.tiles_x;
-      t /= p.tiles_x;
-      int ty = t % p.tiles_y;
-      int b = t / p.tiles_y;
+      int n, tx, ty, b;
+      decode_tile(p, tile, n, tx, ty, b);
       const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
       const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho);
       mbar_wait(tfull_bar(as), aphase);
@@ -288,6 +280,12 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   p.Ho = d->Ho;
   p.Wo = d->Wo;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n_tiles * d->B;
+  DB_REQUIRE((long long)p.tiles_x * p.tiles_y * p.n_tiles * d->B < (1ll << 24) && p.tiles_x < 65536 &&
+                 p.tiles_y < 65536 && p.n_tiles < 65536,
+             "conv: too many tiles for one launch (%d x %d x %d x %d)", p.tiles_x, p.tiles_y, p.n_tiles, d->B);
+  p.mg_n = div_magic(p.n_tiles);
+  p.mg_x = div_magic(p.tiles_x);
+  p.mg_y = div_magic(p.tiles_y);
   p.in_stride = d->in_stride;
   p.taps = d->taps;
   p.kchunks = d->Cin / 64;
