@@ -25,6 +25,7 @@ class ConvDesc(C.Structure):
         ("residual", C.c_void_p),
         ("relu", C.c_int32),
         ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p), ("y_pool", C.c_void_p),
+        ("absmax", C.c_void_p),
     ]
 
 
@@ -63,6 +64,7 @@ _PROTOS = {
     "dreamb200_bn_bwd_apply_f16": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_maxpool3_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dreamb200_scale_mask_bias_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_absmax_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_upsample2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),

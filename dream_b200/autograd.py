@@ -46,11 +46,23 @@ class _HourglassTrainFn(torch.autograd.Function):
         y = models._run_conv(P["first"], t)
         tape.append(("first", "layer_0_1_down.0", t, y))
         t = y
+        sk = model.skip_connections
+        skips = {}
+
+        def add_skip(t, name):
+            """hourglass skip connection (models.py:775-807): out = t + skip; both addends get the gradient"""
+            out = ops.add_(t.clone(), skips[name])
+            tape.append(("add", name, None, None))
+            return out
+
         for bi, (block, idxs, _) in enumerate(models.VGG_TRUNK):
             if bi > 0:
                 y = ops.maxpool(t, 2, 2, 0)
                 tape.append(("pool", None, t, y))
                 t = y
+                if sk:
+                    skips["pool%d" % bi] = t
+                    tape.append(("mark", "pool%d" % bi, None, None))
             for j in idxs:
                 if block == "layer_0_1_down" and j == 0:
                     continue
@@ -58,8 +70,14 @@ class _HourglassTrainFn(torch.autograd.Function):
                 y = models._run_conv(P[key], t)
                 tape.append(("conv", key, t, y))
                 t = y
+            if sk and block == "layer_0_1_down":
+                skips["x_0_1"] = t
+                tape.append(("mark", "x_0_1", None, None))
+        if sk:
+            t = add_skip(t, "pool4")
         if model.deconv_decoder:
             # ConvTranspose2d(3, s2, p1, op1) + ReLU (+ conv3x3 + ReLU), models.py:618-686
+            after = {"deconv_0_4": "pool3", "deconv_0_3": "pool2", "deconv_0_2": "pool1", "deconv_0_1": "x_0_1"}
             for name in ("deconv_0_4", "deconv_0_3", "deconv_0_2", "deconv_0_1"):
                 y = models._run_deconv(P[name + ".0"], t)
                 tape.append(("deconv", name + ".0", t, y))
@@ -68,6 +86,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                     y = models._run_conv(P[name + ".2"], t)
                     tape.append(("conv", name + ".2", t, y))
                     t = y
+                if sk:
+                    t = add_skip(t, after[name])
         else:
             stages = [("upsample_0_4", ".4", ".6"), ("upsample_0_3", ".4", ".6")]
             if model.full_output:
@@ -80,6 +100,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                     y = models._run_conv(P[name + suffix], t)
                     tape.append(("conv", name + suffix, t, y))
                     t = y
+                if sk and name == "upsample_0_4":
+                    t = add_skip(t, "pool3")
         for key in ("heads_0.0", "heads_0.2"):
             y = models._run_conv(P[key], t)
             tape.append(("conv", key, t, y))
@@ -104,17 +126,29 @@ class _HourglassTrainFn(torch.autograd.Function):
         amax = go.abs().amax().clamp_min(1e-30)
         cum = torch.exp2(torch.floor(torch.log2(256.0 / amax))).reshape(1)
         g = ops.nchw_to_nhwc_f16((go * cum).contiguous(), 64)           # [B,h,w,64], channels >= K are zero
+        amax = ops.absmax(g)            # later layers get max|dY| for free from the producing data-gradient kernel
+        stash = {}                      # skip connections: gradient of the skip addend, with the scale it carries
         for kind, key, xin, yout in reversed(tape):
+            if kind == "add":
+                stash[key] = (g.clone(), cum.clone())
+                continue
+            if kind == "mark":
+                sg, scum = stash.pop(key)
+                ops.scale_mask_(sg, None, cum / scum)           # bring it to the current loss scale, then accumulate
+                ops.add_(g, sg)
+                amax = ops.absmax(g)
+                continue
             if kind in ("conv", "head", "first"):
                 node = models._node_for(model, key)
                 pc = P["first"] if kind == "first" else P[key]
-                f = torch.exp2(torch.floor(torch.log2(256.0 / ops.absmax(g).clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
-                ops.scale_mask_(g, yout if pc.relu else None, f)
+                f = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
                 cum = cum * f
                 inv = 1.0 / cum
                 cout, cin = node.weight.shape[0], node.weight.shape[1]
+                # ReLU mask + re-scaling + bias gradient in one pass over dY
+                db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
                 if node.bias is not None:
-                    grads[key + ".bias"] = ops.bias_grad(g)[:cout] * inv
+                    grads[key + ".bias"] = db[:cout] * inv
                 if kind == "first":
                     dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]                   # [co, (r,s,c)]
                     grads[key + ".weight"] = (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
@@ -125,7 +159,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
                     B, H, W, _ = xin.shape
                     g_in = g
-                    g = ops.conv_taps(g, wd, None, taps, H, W)
+                    amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
+                    g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax)
                     if DEBUG_CAPTURE is not None:
                         DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))   # g is re-scaled in place later
                 if kind == "first" and DEBUG_CAPTURE is not None:
@@ -133,13 +168,13 @@ class _HourglassTrainFn(torch.autograd.Function):
             elif kind == "deconv":
                 node = models._node_for(model, key)
                 pc = P[key]
-                f = torch.exp2(torch.floor(torch.log2(256.0 / ops.absmax(g).clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
-                ops.scale_mask_(g, yout if pc.relu else None, f)
+                f = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
                 cum = cum * f
                 inv = 1.0 / cum
                 cin, cout = node.weight.shape[0], node.weight.shape[1]          # ConvTranspose2d: [Cin, Cout, 3, 3]
+                db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
                 if node.bias is not None:
-                    grads[key + ".bias"] = ops.bias_grad(g)[:cout] * inv
+                    grads[key + ".bias"] = db[:cout] * inv
                 # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
                 dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
                 grads[key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
@@ -148,22 +183,19 @@ class _HourglassTrainFn(torch.autograd.Function):
                 wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
                 B, H, W, _ = xin.shape
                 g_in = g
-                g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2)
+                amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
+                g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2, absmax=amax)
                 if DEBUG_CAPTURE is not None:
                     DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))
             elif kind == "pool":
                 g = ops.maxpool2_bwd(xin, g)
             elif kind == "up":
-                g = ops.upsample2_bwd(g)
+                g = ops.upsample2_bwd(g)        # sums 4 values: the stale `amax` can under-estimate by <= 4x (256x headroom)
         ctx.tape = None
         return (None, None) + tuple(grads.get(n) for n in ctx.param_names)
 
 
 def hourglass_train_forward(model, x):
-    if model.skip_connections:
-        raise NotImplementedError(
-            "dream_b200 training covers DreamHourglass with the upsample or the deconv decoder (vgg-Q / vgg-F); "
-            "skip_connections training is not built yet (inference is).")
     x = model._check_input(x)
     params = [p for _, p in model.named_parameters()]
     return _HourglassTrainFn.apply(model, x, *params)

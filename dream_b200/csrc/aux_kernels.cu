@@ -39,45 +39,62 @@ static int grid_for(long long work_items, int threads) {
 
 // ---------------------------------------------------------------------------------------------
 // First-layer patch gather: x fp32 NCHW [B,3,H,W] -> fp16 [B,Ho,Wo,Kpad], k = (r*S+s)*3 + c.
-// One thread produces 8 consecutive k (one 16 B store).  Reads hit L1/L2 (each input pixel is
-// reused R*S times by neighbouring threads).
+// A block step handles 32 consecutive output pixels: warp w gathers k-group w (8 consecutive k) for the 32
+// pixels (lane = pixel, so the fp32 reads are coalesced along x), the 16-byte results cross through shared
+// memory, and the block then writes the 32 x Kpad/8 chunks as one contiguous, fully coalesced run.
 // ---------------------------------------------------------------------------------------------
-__global__ void im2col_first_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int H,
-                                    int W, int R, int S, int stride, int pad, int Ho, int Wo, int Kpad) {
-  const int kgroups = Kpad / 8;
-  const long long total = (long long)B * Ho * Wo * kgroups;
-  const int K = R * S * 3;
+template <int R, int S>
+__global__ void __launch_bounds__(256)
+im2col_first_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int stride, int pad,
+                    int Ho, int Wo, int Kpad) {
+  constexpr int K = R * S * 3;
+  const int kgroups = Kpad / 8;                       // <= 24 (Kpad <= 192)
+  __shared__ uint4 tile[32][25];
+  const long long npix = (long long)B * Ho * Wo;
+  const long long nsteps = (npix + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t plane = (size_t)H * W;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int kg = (int)(idx % kgroups);
-    long long pix = idx / kgroups;
-    const int ox = (int)(pix % Wo);
-    pix /= Wo;
-    const int oy = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
-      float f = 0.0f;
-      if (k < K) {
-        const int c = k % 3;
-        const int rs = k / 3;
-        const int r = rs / S, s = rs - r * S;
-        const int iy = oy * stride - pad + r, ix = ox * stride - pad + s;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-          f = __ldg(x + ((size_t)b * 3 + c) * plane + (size_t)iy * W + ix);
-      }
-      v[j] = f;
+  for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+    const long long pix = step * 32 + lane;
+    const bool pvalid = pix < npix;
+    int ox = 0, oy = 0, b = 0;
+    if (pvalid) {
+      ox = (int)(pix % Wo);
+      const long long r = pix / Wo;
+      oy = (int)(r % Ho);
+      b = (int)(r / Ho);
     }
-    uint4 o;
-    __half2 h;
-    h = __floats2half2_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-    out[idx] = o;
+    const float* xb = x + (size_t)b * 3 * plane;
+    for (int kg = warp; kg < kgroups; kg += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = kg * 8 + j;
+        float f = 0.0f;
+        if (pvalid && k < K) {
+          const int c = k % 3;
+          const int rs = k / 3;
+          const int r = rs / S, s_ = rs - r * S;
+          const int iy = oy * stride - pad + r, ix = ox * stride - pad + s_;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) f = __ldg(xb + c * plane + (size_t)iy * W + ix);
+        }
+        v[j] = f;
+      }
+      uint4 o;
+      __half2 h;
+      h = __floats2half2_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+      tile[lane][kg] = o;
+    }
+    __syncthreads();
+    const int chunks = 32 * kgroups;
+    for (int i = threadIdx.x; i < chunks; i += 256) {
+      const int pl = i / kgroups, kg = i - pl * kgroups;
+      if (step * 32 + pl < npix) out[(size_t)step * 32 * kgroups + i] = tile[pl][kg];
+    }
+    __syncthreads();
   }
 }
 
@@ -221,9 +238,17 @@ extern "C" int dreamb200_im2col_first(const float* x, void* out, int B, int H, i
   DB_REQUIRE(x && out, "im2col_first: null pointer");
   DB_REQUIRE(Kpad % 8 == 0 && Kpad >= R * S * 3, "im2col_first: Kpad=%d too small / unaligned", Kpad);
   DB_REQUIRE(B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "im2col_first: empty tensor");
-  const long long total = (long long)B * Ho * Wo * (Kpad / 8);
-  im2col_first_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<uint4*>(out), B, H, W, R, S, stride, pad, Ho, Wo, Kpad);
+  DB_REQUIRE(Kpad <= 192, "im2col_first: Kpad=%d > 192", Kpad);
+  DB_REQUIRE((R == 3 && S == 3) || (R == 7 && S == 7), "im2col_first: only 3x3 and 7x7 first layers exist (got %dx%d)",
+             R, S);
+  const long long steps = ((long long)B * Ho * Wo + 31) / 32;
+  const int grid = grid_for(steps * 256, 256);
+  if (R == 3)
+    im2col_first_kernel<3, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint4*>(out), B, H, W,
+                                                                     stride, pad, Ho, Wo, Kpad);
+  else
+    im2col_first_kernel<7, 7><<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint4*>(out), B, H, W,
+                                                                     stride, pad, Ho, Wo, Kpad);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

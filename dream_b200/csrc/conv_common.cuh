@@ -27,6 +27,7 @@ struct ConvParams {
   int store_full;   // also store the un-pooled tile through tmC
   // division-free tile decode: q = (x * magic) >> 40 is exact for x < 2^24, divisor < 2^16 (host: 2^40/d + 1)
   unsigned long long mg_n, mg_x, mg_y;
+  float* absmax;    // optional: running max |output| (bits of a non-negative float), see dreamb200_conv_desc
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
@@ -139,6 +140,18 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      }
+      if (p.absmax != nullptr) {
+        float m = 0.0f;
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(f[i]));
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) {
+          if (!(m <= 3.0e38f)) m = 3.0e38f;
+          atomicMax(reinterpret_cast<int*>(p.absmax), __float_as_int(m));
+        }
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) hv[hh * 16 + i] = pack_h2(f[2 * i], f[2 * i + 1]);

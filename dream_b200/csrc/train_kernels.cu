@@ -243,6 +243,41 @@ __global__ void scale_mask_kernel(uint4* __restrict__ dy, const uint4* __restric
   }
 }
 
+// dy = dy * scale * (y > 0) AND db[c] += sum_rows dy (after masking): ReLU backward, loss re-scaling and the bias
+// gradient in ONE pass over dY.  dy / y fp16 [rows, C]; block = 32 channel pairs x 8 row lanes like bias_grad_kernel.
+__global__ void scale_mask_bias_kernel(__half* __restrict__ dy, const __half* __restrict__ y,
+                                       const float* __restrict__ scale, float* __restrict__ db, long long rows, int C) {
+  const int cg = blockIdx.y;
+  const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+  const int c = cg * 64 + tc * 2;
+  const float sc = scale != nullptr ? __ldg(scale) : 1.0f;
+  float a0 = 0.0f, a1 = 0.0f;
+  for (long long r = (long long)blockIdx.x * 8 + tr; r < rows; r += (long long)gridDim.x * 8) {
+    __half2* gp = reinterpret_cast<__half2*>(dy + (size_t)r * C + c);
+    float2 g = __half22float2(*gp);
+    g.x *= sc; g.y *= sc;
+    if (y != nullptr) {
+      const float2 yv = __half22float2(*reinterpret_cast<const __half2*>(y + (size_t)r * C + c));
+      if (!(yv.x > 0.0f)) g.x = 0.0f;
+      if (!(yv.y > 0.0f)) g.y = 0.0f;
+    }
+    const __half2 gh = __floats2half2_rn(g.x, g.y);
+    *gp = gh;
+    const float2 gr = __half22float2(gh);          // sum what the consumers will read
+    a0 += gr.x; a1 += gr.y;
+  }
+  __shared__ float sh[8][64];
+  sh[tr][tc * 2] = a0;
+  sh[tr][tc * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += sh[i][threadIdx.x];
+    atomicAdd(db + cg * 64 + threadIdx.x, v);
+  }
+}
+
 // out = max(out, max |x|) over an fp16 tensor; `out` holds the bits of a non-negative float (zeroed by the caller)
 __global__ void absmax_kernel(const uint4* __restrict__ x, long long n8, int* __restrict__ out) {
   float m = 0.0f;
@@ -631,6 +666,20 @@ extern "C" int dreamb200_scale_mask_f16(void* dy, const void* y, const float* sc
   DB_REQUIRE(dy && n > 0 && n % 8 == 0, "scale_mask: bad arguments");
   scale_mask_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<uint4*>(dy), reinterpret_cast<const uint4*>(y), scale, n / 8);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const float* scale, float* db, long long rows,
+                                             int C, void* stream) {
+  DB_REQUIRE(dy && db && rows > 0 && C % 64 == 0, "scale_mask_bias: bad arguments");
+  long long bx = (rows + 8 * 16 - 1) / (8 * 16);
+  if (bx > 148 * 8) bx = 148 * 8;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)(C / 64));
+  scale_mask_bias_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__half*>(dy),
+                                                                 reinterpret_cast<const __half*>(y), scale, db, rows, C);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -31,7 +31,7 @@ def round_up(v, m):
 
 
 def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
-              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None):
+              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None, absmax=None):
     """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
 
     x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
@@ -80,6 +80,9 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         assert tuple(residual.shape) == (B, Ho, Wo, Cout_pad)
         d.residual = residual.data_ptr()
     d.relu = 1 if relu else 0
+    if absmax is not None:          # 1-element fp32 cuda tensor (zeroed): receives max |y| of this launch
+        assert absmax.dtype == torch.float32 and absmax.numel() == 1 and head_cout is None
+        d.absmax = absmax.data_ptr()
     for name, t in (("residual_f32", residual_f32), ("y_f32", y_f32)):
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, Ho, Wo, Cout_pad)
@@ -270,6 +273,16 @@ def scale_mask_(dy, y=None, scale=None):
 
 def relu_mask_(dy, y):
     return scale_mask_(dy, y)
+
+
+def scale_mask_bias_(dy, y=None, scale=None):
+    """scale_mask_ fused with the bias gradient: returns db[c] = sum over pixels of the updated dy (fp32 [C])."""
+    assert dy.dtype == torch.float16 and dy.is_contiguous()
+    Cc = dy.shape[-1]
+    db = torch.zeros((Cc,), dtype=torch.float32, device=dy.device)
+    check(lib().dreamb200_scale_mask_bias_f16(_ptr(dy), _ptr(y), _ptr(scale), _ptr(db), dy.numel() // Cc, Cc,
+                                              _stream()), "dreamb200_scale_mask_bias_f16")
+    return db
 
 
 def absmax(x):

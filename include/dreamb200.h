@@ -59,6 +59,9 @@ typedef struct dreamb200_conv_desc {
   /* fused nn.MaxPool2d(2) (models.py:589): when set, the 2x2/s2 (floor) max pool of the output is written
      here, fp16 NHWC dense [B,Ho/2,Wo/2,Cout_pad]; `y` may then be NULL (un-pooled tensor not stored). */
   void* y_pool;
+  /* when set: *absmax = max(*absmax, max |y|) over the fp16 outputs written by this launch (device float holding a
+     non-negative value, zeroed by the caller) -- lets the backward pass pick the next layer's loss scale for free */
+  float* absmax;
 } dreamb200_conv_desc;
 
 /* fraction of the 128 accumulator rows a conv with this output size keeps busy, for the free tile
@@ -130,6 +133,9 @@ int dreamb200_maxpool3_bwd_nhwc(const void* x, const void* dy, void* dx, int B, 
 /* dy = dy * (*scale) * (y > 0): autograd of nn.ReLU given its output, fused with the power-of-two
    re-scaling that keeps fp16 gradients in range; y and/or scale may be NULL */
 int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream);
+/* scale_mask and the bias gradient in one pass: dy = dy*(*scale)*(y>0); db[c] += sum_rows dy (caller zeroes db) */
+int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const float* scale, float* db, long long rows, int C,
+                                  void* stream);
 /* *out = max(*out, max|x|) over n fp16 values (out: device float, zeroed by the caller) */
 int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream);
 /* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C] */

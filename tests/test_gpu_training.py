@@ -173,14 +173,18 @@ def test_backward_kernels_layerwise_teacher_forced(arch, built_lib):
     assert checked == (25 if arch == "vgg_f" else 22)
 
 
-def test_vgg_f_training_gradients_track_oracle(built_lib):
-    """vgg-F (deconv decoder, full-resolution output): loss and gradient direction / norm vs the oracle's autograd."""
+@pytest.mark.parametrize("kw", [dict(deconv_decoder=True, full_output=True), dict(skip_connections=True),
+                                dict(deconv_decoder=True, full_output=True, skip_connections=True)])
+def test_vgg_f_training_gradients_track_oracle(kw, built_lib):
+    """vgg-F (deconv decoder, full-resolution output) and the hourglass skip connections (models.py:775-807):
+    loss and gradient direction / norm vs the oracle's autograd."""
     from dream_b200 import models
-    kw = dict(deconv_decoder=True, full_output=True)
-    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix="", **kw), seed=6, out_gain=13.0, mode="default")
+    skw = {k: v for k, v in kw.items() if k != "skip_connections"}
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix="", **skw), seed=6, out_gain=13.0, mode="default")
     gen = torch.Generator().manual_seed(4)
     x = torch.rand((2, 3, 48, 64), generator=gen) * 2 - 1
-    target = torch.rand((2, 7, 48, 64), generator=gen)
+    out_hw = (48, 64) if kw.get("full_output") else (12, 16)
+    target = torch.rand((2, 7) + out_hw, generator=gen)
     ref_loss, ref_grads, _ = _oracle_grads(sd, x, target, **kw)
     net = models.DreamHourglass(7, internalize_spatial_softmax=False, **kw)
     net.load_state_dict(sd)
@@ -348,3 +352,32 @@ def test_training_steps_track_oracle_loss_curve(built_lib):
         ref.backward()
         opt.step()
         assert abs(loss.item() - ref.item()) <= 5e-3 * ref.item(), (step, loss.item(), ref.item())
+
+
+def test_fused_scale_mask_bias_and_epilogue_absmax(built_lib):
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    dy = torch.randn((2, 30, 41, 128), device="cuda", generator=g).half()
+    y = torch.relu(torch.randn((2, 30, 41, 128), device="cuda", generator=g)).half()
+    sc = torch.full((1,), 8.0, device="cuda")
+    ref = (dy.float() * 8.0 * (y.float() > 0)).half()
+    d2 = dy.clone()
+    db = ops.scale_mask_bias_(d2, y, sc)
+    assert torch.equal(d2, ref)
+    assert (db - ref.float().sum(dim=(0, 1, 2))).abs().max() <= 1e-3 * ref.float().abs().sum(dim=(0, 1, 2)).max()
+    # max |y| from the conv epilogue
+    x = (torch.randn((2, 33, 47, 64), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((128, 64, 3, 3), device="cuda", generator=g) * 0.05
+    wp = ops.pack_conv_weight(w, [(r, s) for r in range(3) for s in range(3)])
+    am = torch.zeros((1,), device="cuda")
+    out = ops.conv_taps(x, wp, None, ops.TAPS_3x3, 33, 47, absmax=am)
+    assert abs(am.item() - out.float().abs().max().item()) <= 2e-3 * am.item()
+    # the faster patch gather equals an explicit unfold
+    xin = torch.rand((2, 3, 21, 30), device="cuda", generator=g) * 2 - 1
+    for (R, stride, pad, Kp) in ((3, 1, 1, 64), (7, 2, 3, 192)):
+        got = ops.im2col_first(xin, R, R, stride, pad, Kp)
+        unf = torch.nn.functional.unfold(xin.half().float(), R, padding=pad, stride=stride)   # [B, 3*R*R, L] (c, r, s)
+        Ho, Wo = got.shape[1], got.shape[2]
+        unf = unf.view(2, 3, R * R, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(2, Ho, Wo, R * R * 3)   # k = (r*S+s)*3 + c
+        assert torch.equal(got[..., :R * R * 3].float(), unf)
+        assert float(got[..., R * R * 3:].abs().max()) == 0.0
