@@ -133,6 +133,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                 stash[key] = (g.clone(), cum.clone())
                 continue
             if kind == "mark":
+                if key not in stash:            # this tensor was not used as a skip by the configured decoder
+                    continue
                 sg, scum = stash.pop(key)
                 ops.scale_mask_(sg, None, cum / scum)           # bring it to the current loss scale, then accumulate
                 ops.add_(g, sg)
