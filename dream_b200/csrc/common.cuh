@@ -219,6 +219,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major, SWIZZLE_128B, explicit K-group stride (SBO): lets the K rows (pixels) of one 8-pixel image row sit
+// `sbo_bytes` apart from the next image row's -- a window into a wider "halo" slab.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_sbo(uint32_t smem_addr, uint32_t mn_chunk_bytes,
+                                                           uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((mn_chunk_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // same as umma_idesc_f16_m128 but both operands MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t umma_idesc_f16_m128_mn(uint32_t n) {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);

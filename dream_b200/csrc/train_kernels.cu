@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "dreamb200.h"
 
+#include <stdlib.h>
+
 namespace db200 {
 
 int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
@@ -187,6 +189,207 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradPa
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad for the standard 3x3 / stride 1 / pad 1 convolution: one CTA owns a kernel ROW r (its three taps s).
+// Per 8x16-pixel k-block it loads the dY tile once (it is the same for every tap) and ONE 10x16-pixel slab of X
+// per 64-channel chunk; the B operand of tap (r, s) is that slab read from byte offset s*128 with 1280 B between
+// image rows (the hardware swizzles on the absolute shared-memory address, see conv_rs.cu).  Three accumulators
+// (s = 0,1,2) of BLOCK_N columns live in TMEM.  2.5x fewer bytes per MMA than the generic per-tap kernel above.
+// ---------------------------------------------------------------------------------------------
+struct Wgrad3Params {
+  int B, H, W;
+  int tiles_x, tiles_y;
+  int co_tiles, ci_tiles, splits;
+  long long kblocks_total;
+  float* dw;
+  int Cout_pad, Cin_pad;
+  int stages;
+};
+
+constexpr int kW3SlabBytes = 16 * 1280;      // 16 image rows x 10 pixels x 128 B
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ Wgrad3Params p) {
+  constexpr int kABytes = 2 * kChunkBytes;
+  constexpr int kBBytes = (BLOCK_N / 64) * kW3SlabBytes;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = 3 * BLOCK_N <= 256 ? 256 : 512;
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128_mn(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * stages);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // unit of this CTA: (split, kernel row r, co tile, ci tile); CTAs of one split are adjacent (shared L2 lines)
+  int u = blockIdx.x;
+  const int ci_t = u % p.ci_tiles; u /= p.ci_tiles;
+  const int co_t = u % p.co_tiles; u /= p.co_tiles;
+  const int r = u % 3;
+  const int split = u / 3;
+  const long long kb_lo = p.kblocks_total * split / p.splits;
+  const long long kb_hi = p.kblocks_total * (split + 1) / p.splits;
+  const int n_kb = (int)(kb_hi - kb_lo);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int tiles = p.tiles_x * p.tiles_y;
+      for (long long kb = kb_lo; kb < kb_hi; ++kb) {
+        const int b = (int)(kb / tiles);
+        const int rr = (int)(kb - (long long)b * tiles);
+        const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+        const int x0 = tx * 8, y0 = ty * 16;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, x0, y0, b);
+#pragma unroll
+        for (int n = 0; n < BLOCK_N / 64; ++n)
+          tma_load_4d(sa + kABytes + n * kW3SlabBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, x0 - 1,
+                      y0 + r - 1, b);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
+            const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, kChunkBytes);
+            const uint64_t bdesc =
+                umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j) * 1280u + (uint32_t)s * 128u, kW3SlabBytes, 1280u);
+            umma_f16(tmem_base + (uint32_t)(s * BLOCK_N), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else if (n_kb > 0) {
+    const int q = warp & 3;
+    const int co = co_t * 128 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int s = 0; s < 3; ++s) {
+      float* out = p.dw + ((size_t)(r * 3 + s) * p.Cout_pad + co) * p.Cin_pad + ci_t * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * BLOCK_N + c * 32), v);
+        tmem_wait_ld();
+        if (co < p.Cout_pad) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(out + c * 32 + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_wgrad3(const CUtensorMap& tmDY, const CUtensorMap& tmX, Wgrad3Params& p, cudaStream_t stream) {
+  constexpr int kStageBytes = 2 * kChunkBytes + (BLOCK_N / 64) * kW3SlabBytes;
+  int stages = (232448 - 1024 - 512) / kStageBytes;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * kStageBytes + 512;
+  auto kern = wgrad3x3_kernel<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int grid = p.splits * 3 * p.co_tiles * p.ci_tiles;
+  kern<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static int wgrad3x3_impl(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
+                         cudaStream_t stream) {
+  Wgrad3Params p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = (W + 7) / 8;
+  p.tiles_y = (H + 15) / 16;
+  const int block_n = Cin_pad % 128 == 0 ? 128 : 64;
+  p.co_tiles = (Cout_pad + 127) / 128;
+  p.ci_tiles = Cin_pad / block_n;
+  p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
+  const int units = 3 * p.co_tiles * p.ci_tiles;
+  int splits = (device_sm_count() + units - 1) / units;
+  if (splits < 1) splits = 1;
+  if ((long long)splits > p.kblocks_total) splits = (int)p.kblocks_total;
+  p.splits = splits;
+  p.dw = dw;
+  p.Cout_pad = Cout_pad;
+  p.Cin_pad = Cin_pad;
+  CUtensorMap tmDY, tmX;
+  const uint32_t es[4] = {1, 1, 1, 1};
+  {
+    const uint32_t box[4] = {64, 8, 16, 1};
+    uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cout_pad * 2, (uint64_t)W * Cout_pad * 2, (uint64_t)H * W * Cout_pad * 2};
+    if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad3 dY")) return -1;
+  }
+  {
+    const uint32_t box[4] = {64, 10, 16, 1};
+    uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
+    if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad3 X")) return -1;
+  }
+  if (block_n == 128) return launch_wgrad3<128>(tmDY, tmX, p, stream);
+  return launch_wgrad3<64>(tmDY, tmX, p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,6 +834,15 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
 
 extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
                                int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
+  static int use_row_kernel = -1;
+  if (use_row_kernel < 0) {
+    const char* e = getenv("DREAMB200_WGRAD3");       // 0 disables the row-shared 3x3 kernel (A/B measurements)
+    use_row_kernel = e ? atoi(e) : 1;
+  }
+  bool std3x3 = use_row_kernel && taps == 9 && dy && x && dw && tap_dy && tap_dx && Cout_pad % 64 == 0 &&
+                Cin_pad % 64 == 0 && B > 0 && H > 0 && W > 0;
+  for (int t = 0; std3x3 && t < 9; ++t) std3x3 = tap_dy[t] == t / 3 - 1 && tap_dx[t] == t % 3 - 1;
+  if (std3x3) return wgrad3x3_impl(dy, x, dw, B, H, W, Cout_pad, Cin_pad, (cudaStream_t)stream_v);
   return wgrad_impl(dy, x, dw, B, H, W, H, W, H, W, 1, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
                     (cudaStream_t)stream_v);
 }
