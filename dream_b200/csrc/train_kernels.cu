@@ -367,8 +367,8 @@ static int wgrad3x3_impl(const void* dy, const void* x, float* dw, int B, int H,
   p.ci_tiles = Cin_pad / block_n;
   p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
   const int units = 3 * p.co_tiles * p.ci_tiles;
-  int splits = (device_sm_count() + units - 1) / units;
-  if (splits < 1) splits = 1;
+  int splits = device_sm_count() / units;          // floor: the whole grid must be ONE wave (1 CTA per SM) --
+  if (splits < 1) splits = 1;                      // a few CTAs spilling into a second wave double the kernel time
   if ((long long)splits > p.kblocks_total) splits = (int)p.kblocks_total;
   p.splits = splits;
   p.dw = dw;
@@ -803,8 +803,8 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
   p.ci_tiles = Cin_pad / block_n;
   p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
   const int units = taps * p.co_tiles * p.ci_tiles;
-  int splits = (device_sm_count() + units - 1) / units;
-  if (splits < 1) splits = 1;
+  int splits = device_sm_count() / units;          // floor: the whole grid must be ONE wave (1 CTA per SM) --
+  if (splits < 1) splits = 1;                      // a few CTAs spilling into a second wave double the kernel time
   if ((long long)splits > p.kblocks_total) splits = (int)p.kblocks_total;
   p.splits = splits;
   p.dw = dw;
