@@ -395,35 +395,6 @@ static int wgrad3x3_impl(const void* dy, const void* x, float* dw, int B, int H,
 // ---------------------------------------------------------------------------------------------
 // streaming kernels
 // ---------------------------------------------------------------------------------------------
-// NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp = W rounded up to 8, pad columns zero)
-__global__ void nhwc_to_cm_f16_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W,
-                                      int C, int Wp) {
-  __shared__ __half tile[32][34];
-  const int xtiles = (Wp + 31) / 32, ctiles = C / 32;
-  const long long total = (long long)B * H * xtiles * ctiles;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-    const int ct = (int)(t % ctiles);
-    long long r = t / ctiles;
-    const int xt = (int)(r % xtiles);
-    r /= xtiles;
-    const int yy = (int)(r % H);
-    const int b = (int)(r / H);
-    for (int i = ty; i < 32; i += 8) {
-      const int xx = xt * 32 + i;
-      __half v = __float2half(0.0f);
-      if (xx < W) v = x[((size_t)((size_t)b * H + yy) * W + xx) * C + ct * 32 + tx];
-      tile[i][tx] = v;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-      const int xx = xt * 32 + tx;
-      if (xx < Wp) y[((size_t)((size_t)b * C + ct * 32 + i) * H + yy) * Wp + xx] = tile[tx][i];
-    }
-    __syncthreads();
-  }
-}
-
 // dy = dy * scale * (y > 0): ReLU backward fused with the dynamic loss re-scaling; y and scale optional
 __global__ void scale_mask_kernel(uint4* __restrict__ dy, const uint4* __restrict__ y, const float* __restrict__ scale,
                                   long long n8) {
@@ -861,17 +832,6 @@ extern "C" int dreamb200_wgrad_strided(const void* dy, const void* x, float* dw,
                                        void* stream_v) {
   return wgrad_impl(dy, x, dw, B, Ho, Wo, Ho, Wo, Hx, Wx, 1, 2, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
                     (cudaStream_t)stream_v);
-}
-
-extern "C" int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream) {
-  DB_REQUIRE(x && y, "nhwc_to_cm: null pointer");
-  DB_REQUIRE(C % 32 == 0 && Wp % 8 == 0 && Wp >= W, "nhwc_to_cm: bad C=%d / Wp=%d", C, Wp);
-  const long long tiles = (long long)B * H * ((Wp + 31) / 32) * (C / 32);
-  nhwc_to_cm_f16_kernel<<<grid_cap(tiles * 256, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), B, H, W, C, Wp);
-  DB_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
 }
 
 extern "C" int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long long n, void* stream) {

@@ -228,15 +228,6 @@ def pad_bias(b, cout_pad, device):
 # ----------------------------------------------------------------------------------------------
 # backward (training) wrappers
 # ----------------------------------------------------------------------------------------------
-def nhwc_to_cm(x):
-    """NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] with Wp = round_up(W, 8) (zero padded)."""
-    B, H, W_, Cc = x.shape
-    Wp = round_up(W_, 8)
-    y = torch.empty((B, Cc, H, Wp), dtype=torch.float16, device=x.device)
-    check(lib().dreamb200_nhwc_to_cm_f16(_ptr(x), _ptr(y), B, H, W_, Cc, Wp, _stream()), "dreamb200_nhwc_to_cm_f16")
-    return y
-
-
 def wgrad(dy, x, taps, deconv=False):
     """dW[tap][co][ci] = sum_p dy[p][co] * x[p + tap][ci]; dy/x NHWC fp16 of equal H, W -> fp32 [T,Co,Ci].
     deconv=True: stride-2 ConvTranspose weight gradient, dy on the 2x finer grid: sum_p dy[2p + tap][co] * x[p][ci]."""

@@ -102,8 +102,6 @@ int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* g
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
 
 /* ---- backward (training) ------------------------------------------------------------------ */
-/* NHWC fp16 [B,H,W,C] -> channel-major fp16 [B,C,H,Wp] (Wp % 8 == 0, pad columns zeroed); utility */
-int dreamb200_nhwc_to_cm_f16(const void* x, void* y, int B, int H, int W, int C, int Wp, void* stream);
 /* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy, x NHWC fp16 [B,H,W,Cout_pad|Cin_pad],
    dw fp32 [taps][Cout_pad][Cin_pad] (caller zeroes it); autograd of nn.Conv2d weights */
 int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
