@@ -42,6 +42,9 @@ _PROTOS = {
     "dreamb200_conv_tile_utilization": (C.c_double, [C.c_int] * 4),
     "dreamb200_conv2d_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "dreamb200_first_conv3x3": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
+    "dreamb200_first_conv3x3_u8": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p]),
+    "dreamb200_normalize_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 3),
+    "dreamb200_belief_targets": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3),
     "dreamb200_im2col_first": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
     "dreamb200_maxpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "dreamb200_upsample2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),

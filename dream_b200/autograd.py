@@ -42,9 +42,17 @@ class _HourglassTrainFn(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         P = model.plan()
         tape = []          # (kind, key, input, output)
-        t = ops.im2col_first(x, 3, 3, 1, 1, 64)
-        y = models._run_conv(P["first"], t)
-        tape.append(("first", "layer_0_1_down.0", t, y))
+        if model.n_image_input_channels == 3:
+            t = ops.im2col_first(x, 3, 3, 1, 1, 64)
+            y = models._run_conv(P["first"], t)
+            tape.append(("first", "layer_0_1_down.0", t, y))
+        else:
+            # stage >= 2 of DreamHourglassMultiStage: image + previous belief maps, packed to 64 channels; an
+            # ordinary conv layer whose data gradient is handed back to autograd ("input" entry below)
+            t = ops.nchw_to_nhwc_f16(x, 64)
+            y = models._run_conv(P["first"], t)
+            tape.append(("input", None, None, None))
+            tape.append(("conv", "layer_0_1_down.0", t, y))
         t = y
         sk = model.skip_connections
         skips = {}
@@ -111,6 +119,7 @@ class _HourglassTrainFn(torch.autograd.Function):
         ctx.tape = tape
         ctx.model = model
         ctx.param_names = [n for n, _ in model.named_parameters()]
+        ctx.n_in = model.n_image_input_channels
         return out
 
     @staticmethod
@@ -128,7 +137,12 @@ class _HourglassTrainFn(torch.autograd.Function):
         g = ops.nchw_to_nhwc_f16((go * cum).contiguous(), 64)           # [B,h,w,64], channels >= K are zero
         amax = ops.absmax(g)            # later layers get max|dY| for free from the producing data-gradient kernel
         stash = {}                      # skip connections: gradient of the skip addend, with the scale it carries
+        gx = None
         for kind, key, xin, yout in reversed(tape):
+            if kind == "input":
+                if ctx.needs_input_grad[1]:
+                    gx = ops.nhwc_to_nchw_f32(g, ctx.n_in) * (1.0 / cum)
+                continue
             if kind == "add":
                 stash[key] = (g.clone(), cum.clone())
                 continue
@@ -194,7 +208,7 @@ class _HourglassTrainFn(torch.autograd.Function):
             elif kind == "up":
                 g = ops.upsample2_bwd(g)        # sums 4 values: the stale `amax` can under-estimate by <= 4x (256x headroom)
         ctx.tape = None
-        return (None, None) + tuple(grads.get(n) for n in ctx.param_names)
+        return (None, gx) + tuple(grads.get(n) for n in ctx.param_names)
 
 
 def hourglass_train_forward(model, x):

@@ -22,7 +22,9 @@ int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint6
 int device_sm_count();
 
 struct FirstConvParams {
-  const float* x;     // [B,3,H,W] fp32
+  const float* x;     // [B,3,H,W] fp32 (already normalised) ...
+  const uint8_t* xu8; // ... or [B,H,W,3] uint8 frames, normalised on the fly with (u/255 - mean)/std
+  float mean[3], stdv[3];
   const float* bias;  // [64] fp32
   int B, H, W;
   int tiles_x, tiles_y, total_tiles;
@@ -31,6 +33,7 @@ struct FirstConvParams {
 constexpr int kFcThreads = 13 * 32;
 constexpr int kFcTw = 16, kFcTh = 8;
 
+template <bool U8>
 __global__ void __launch_bounds__(kFcThreads, 1)
 first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmC,
                   const __grid_constant__ FirstConvParams p) {
@@ -50,8 +53,15 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const uint32_t w_bar = bar_base + 64u;
   const uint32_t tmem_ptr_smem = bar_base + 72u;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  float* lut = reinterpret_cast<float*>(smem_gen + (bar_base + 128u - smem_base));   // [3][256], U8 only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (U8) {
+    // the same fp32 operations as torchvision's ToTensor + Normalize (dream/datasets.py:60-75), so the fp16
+    // operand is bit-identical to packing the host-normalised fp32 tensor
+    for (int i = threadIdx.x; i < 768; i += kFcThreads)
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), p.mean[i >> 8]), p.stdv[i >> 8]);
+  }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmC);
@@ -86,6 +96,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       const int b = r / p.tiles_y;
       const int ox = tx * kFcTw + lx, oy = ty * kFcTh + ly;
       const float* xb = p.x + (size_t)b * 3 * plane;
+      const uint8_t* ub = p.xu8 + (size_t)b * 3 * plane;
       float v[32];
 #pragma unroll
       for (int k = 27; k < 32; ++k) v[k] = 0.0f;
@@ -100,7 +111,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           const size_t off = (size_t)(ok ? iy : 0) * p.W + (ok ? ix : 0);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float f = __ldg(xb + c * plane + off);
+            const float f = U8 ? lut[c * 256 + __ldg(ub + off * 3 + c)] : __ldg(xb + c * plane + off);
             v[(rr * 3 + ss) * 3 + c] = ok ? f : 0.0f;
           }
         }
@@ -224,14 +235,13 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
 using namespace db200;
 
-// x fp32 NCHW [B,3,H,W]; w fp16 [1][64][64] (k=(r*3+s)*3+c, zero padded); bias fp32 [64]; y fp16 NHWC [B,H,W,64]
-extern "C" int dreamb200_first_conv3x3(const float* x, const void* w, const float* bias, void* y, int B, int H,
-                                       int W, void* stream_v) {
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  DB_REQUIRE(x && w && bias && y, "first_conv: null pointer");
+static int first_conv_launch(const float* x, const uint8_t* xu8, const float* mean3, const float* std3,
+                             const void* w, const float* bias, void* y, int B, int H, int W, cudaStream_t stream) {
+  DB_REQUIRE((x || xu8) && w && bias && y, "first_conv: null pointer");
   DB_REQUIRE(B > 0 && H > 0 && W > 0, "first_conv: empty input");
   FirstConvParams p;
-  p.x = x; p.bias = bias; p.B = B; p.H = H; p.W = W;
+  p.x = x; p.xu8 = xu8; p.bias = bias; p.B = B; p.H = H; p.W = W;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3 ? mean3[c] : 0.0f; p.stdv[c] = std3 ? std3[c] : 1.0f; }
   p.tiles_x = (W + kFcTw - 1) / kFcTw;
   p.tiles_y = (H + kFcTh - 1) / kFcTh;
   p.total_tiles = p.tiles_x * p.tiles_y * B;
@@ -250,16 +260,32 @@ extern "C" int dreamb200_first_conv3x3(const float* x, const void* w, const floa
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmC, y, 4, dims, str, box, es, "first-conv output")) return -1;
   }
-  const int smem_bytes = 1024 + 2 * 16384 + 8192 + 2 * 16384 + 256;
+  const int smem_bytes = 1024 + 2 * 16384 + 8192 + 2 * 16384 + 128 + 3072;
   static bool attr_set = false;
   if (!attr_set) {
-    DB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DB_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  first_conv_kernel<<<grid, kFcThreads, smem_bytes, stream>>>(tmW, tmC, p);
+  if (xu8) first_conv_kernel<true><<<grid, kFcThreads, smem_bytes, stream>>>(tmW, tmC, p);
+  else first_conv_kernel<false><<<grid, kFcThreads, smem_bytes, stream>>>(tmW, tmC, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+// x fp32 NCHW [B,3,H,W]; w fp16 [1][64][64] (k=(r*3+s)*3+c, zero padded); bias fp32 [64]; y fp16 NHWC [B,H,W,64]
+extern "C" int dreamb200_first_conv3x3(const float* x, const void* w, const float* bias, void* y, int B, int H,
+                                       int W, void* stream_v) {
+  DB_REQUIRE(x != nullptr, "first_conv: null input");
+  return first_conv_launch(x, nullptr, nullptr, nullptr, w, bias, y, B, H, W, (cudaStream_t)stream_v);
+}
+
+// same layer fed with raw uint8 HWC frames [B,H,W,3]; mean3/std3 are host pointers (image_normalization)
+extern "C" int dreamb200_first_conv3x3_u8(const void* x_u8, const float* mean3, const float* std3, const void* w,
+                                          const float* bias, void* y, int B, int H, int W, void* stream_v) {
+  DB_REQUIRE(x_u8 && mean3 && std3, "first_conv_u8: null pointer");
+  return first_conv_launch(nullptr, (const uint8_t*)x_u8, mean3, std3, w, bias, y, B, H, W, (cudaStream_t)stream_v);
 }

@@ -103,6 +103,46 @@ def select_keypoints_device(table, next_best_score, sentinel=-999.999):
     return torch.where(take.unsqueeze(1), s[:, :2], torch.full_like(s[:, :2], sentinel))
 
 
+def belief_targets_device(keypoints, image_resolution, sigma=2):
+    """Device form of `create_belief_map` for a whole batch: keypoints fp32 [..., 2]
+    (x, y) in the target frame -- the dataset's `keypoint_projections_output` -- -> CUDA fp32 [..., h, w], equal
+    bit for bit to `torch.tensor(create_belief_map(res, kps)).float()` (dream/datasets.py:196-200).  The stamp
+    values are computed here in fp64 with numpy exactly like the reference and rounded once to fp32."""
+    assert len(image_resolution) == 2, \
+        'Expected "image_resolution" to have length 2, but it has length {}.'.format(len(image_resolution))
+    width, height = int(image_resolution[0]), int(image_resolution[1])
+    kp = torch.as_tensor(keypoints)
+    assert kp.shape[-1] == 2, "expected keypoints [..., 2]"
+    kp = kp.to(device="cuda", dtype=torch.float32).contiguous()
+    n_maps = kp.numel() // 2
+    w = int(sigma * 2)
+    d2 = np.arange(2 * w * w + 1)
+    table = np.ascontiguousarray(np.exp(-(d2 / (2 * (sigma ** 2)))).astype(np.float32))
+    out = torch.empty(tuple(kp.shape[:-1]) + (height, width), dtype=torch.float32, device=kp.device)
+    check(lib().dreamb200_belief_targets(C.c_void_p(kp.data_ptr()), n_maps, height, width, w,
+                                         table.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "dreamb200_belief_targets")
+    return out
+
+
+def normalize_u8_device(frames_u8, mean, std):
+    """uint8 [B,H,W,3] CUDA frames -> fp32 NCHW [B,3,H,W], bit-identical to the dataset's
+    ToTensor + Normalize(mean, std) (dream/datasets.py:60-75,177-179)."""
+    assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 \
+        and frames_u8.shape[3] == 3, "expected a CUDA uint8 batch [B,H,W,3]"
+    x = frames_u8.contiguous()
+    B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    m = np.ascontiguousarray(np.broadcast_to(np.asarray(mean, dtype=np.float32).reshape(-1), (3,)))
+    s = np.ascontiguousarray(np.broadcast_to(np.asarray(std, dtype=np.float32).reshape(-1), (3,)))
+    y = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    check(lib().dreamb200_normalize_u8(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), B, H, W,
+                                       m.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "dreamb200_normalize_u8")
+    return y
+
+
 def create_belief_map(image_resolution, pointsBelief, sigma=2):
     """Training targets (dream/image_proc.py:866-910): one (2*2sigma+1)^2 Gaussian stamp per point
     whose window lies fully inside the frame; returns fp64 [n_points, height, width]."""

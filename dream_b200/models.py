@@ -207,10 +207,25 @@ class _PlanModule(nn.Module):
             self._plan_key = key
         return self._plan
 
+    # (mean[3], stdev[3]) of the config's image_normalization; DreamNetwork sets it.  Only used when the
+    # input is a raw uint8 [B,H,W,3] batch (the dataset's ToTensor + Normalize on device).
+    input_normalization = ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+
+    @staticmethod
+    def _is_raw_frames(x):
+        return x.dtype == torch.uint8
+
     def _check_input(self, x):
-        assert x.dim() == 4 and x.shape[1] == 3, "expected an RGB batch [B,3,H,W], got {}".format(tuple(x.shape))
         if not x.is_cuda:
             raise RuntimeError("dream_b200 runs on a CUDA device only (no CPU fallback); got a CPU tensor")
+        if self._is_raw_frames(x):
+            assert x.dim() == 4 and x.shape[3] == 3, \
+                "expected raw uint8 frames [B,H,W,3], got {}".format(tuple(x.shape))
+            from .image_proc import normalize_u8_device
+            return normalize_u8_device(x, *self.input_normalization)
+        n_in = getattr(self, "n_image_input_channels", 3)
+        assert x.dim() == 4 and x.shape[1] == n_in, \
+            "expected an input batch [B,{},H,W], got {}".format(n_in, tuple(x.shape))
         return x.contiguous().float()
 
 
@@ -225,7 +240,7 @@ class DreamHourglass(_PlanModule):
                  learned_beta=True, initial_beta=1.0, skip_connections=False, deconv_decoder=False,
                  full_output=False):
         super().__init__()
-        assert n_image_input_channels == 3, "only RGB input is supported"
+        assert 1 <= n_image_input_channels <= 64, "the first layer takes 1..64 input channels"
         self.n_keypoints = n_keypoints
         self.n_image_input_channels = n_image_input_channels
         self.internalize_spatial_softmax = internalize_spatial_softmax
@@ -239,7 +254,7 @@ class DreamHourglass(_PlanModule):
         else:
             self.n_output_heads = 1
             self.learned_beta = False
-        cin = 3
+        cin = n_image_input_channels
         for block, idxs, ch in VGG_TRUNK:
             for j in idxs:
                 _add_conv(self, "%s.%d" % (block, j), cin, ch, 3)
@@ -271,8 +286,13 @@ class DreamHourglass(_PlanModule):
     def _build_plan(self):
         P = {}
         first = self._n("layer_0_1_down.0")
-        wf = ops.pack_first_weight(first.weight, 64)
-        P["first"] = _PackedConv(wf, ops.pad_bias(first.bias, 64, wf.device), [(0, 0)], relu=True, cout=64)
+        if self.n_image_input_channels == 3:
+            wf = ops.pack_first_weight(first.weight, 64)
+            P["first"] = _PackedConv(wf, ops.pad_bias(first.bias, 64, wf.device), [(0, 0)], relu=True, cout=64)
+        else:
+            # later stages of DreamHourglassMultiStage see image + previous belief maps (models.py:404-407):
+            # an ordinary 9-tap layer on the input packed to 64 zero-padded channels
+            P["first"] = P["layer_0_1_down.0"] = _pack3x3(first, relu=True, cin_pad=64)
         for block, idxs, _ in VGG_TRUNK:
             for j in idxs:
                 if block == "layer_0_1_down" and j == 0:
@@ -299,10 +319,16 @@ class DreamHourglass(_PlanModule):
         return P
 
     def belief_maps(self, x):
-        """Inference forward: fp32 NCHW [B,3,H,W] (cuda) -> fp32 NCHW belief maps [B,K,h,w]."""
-        x = self._check_input(x)
+        """Inference forward: fp32 NCHW [B,3,H,W] (cuda) -> fp32 NCHW belief maps [B,K,h,w].
+        A uint8 [B,H,W,3] batch is taken as raw frames and normalised inside the first layer's gather."""
         P = self.plan()
-        t = ops.first_conv3x3(x, P["first"].w, P["first"].b)      # gather + pack + conv + bias + ReLU fused
+        if self.n_image_input_channels != 3:
+            t = _run_conv(P["first"], ops.nchw_to_nhwc_f16(self._check_input(x), 64))
+        elif x.is_cuda and self._is_raw_frames(x) and x.dim() == 4 and x.shape[3] == 3:
+            t = ops.first_conv3x3(x.contiguous(), P["first"].w, P["first"].b, u8_norm=self.input_normalization)
+        else:
+            x = self._check_input(x)
+            t = ops.first_conv3x3(x, P["first"].w, P["first"].b)  # gather + pack + conv + bias + ReLU fused
         skips = {}
         sk = self.skip_connections
         pooled = None
@@ -364,6 +390,64 @@ class DreamHourglass(_PlanModule):
         outputs = [out]
         if self.internalize_spatial_softmax:
             outputs.append(self.softmax(out))
+        return outputs
+
+
+class DreamHourglassMultiStage(nn.Module):
+    """dream/models.py:350-553: up to 6 DreamHourglass stages; stage s>1 sees the image concatenated with the
+    previous stage's belief maps (nearest x4 unless the stage already outputs full resolution, :487-493) and
+    `forward` returns the list of every stage's belief maps.  Same constructor keywords and `stageN.*` state-dict
+    names.  Each stage runs the DreamHourglass kernel plan; the concat / x4 replication between stages are
+    plain tensor ops, and in training each stage's autograd node also returns the gradient of its input so the
+    loss on stage s reaches stages < s."""
+
+    def __init__(self, n_keypoints, n_image_input_channels=3, internalize_spatial_softmax=True, learned_beta=True,
+                 initial_beta=1.0, n_stages=2, skip_connections=False, deconv_decoder=False, full_output=False):
+        super().__init__()
+        self.n_keypoints = n_keypoints
+        self.n_image_input_channels = n_image_input_channels
+        self.internalize_spatial_softmax = internalize_spatial_softmax
+        self.skip_connections = skip_connections
+        self.deconv_decoder = deconv_decoder
+        self.full_output = full_output
+        if internalize_spatial_softmax:
+            print("WARNING: Keypoint softmax output head is currently unused. Prefer training new models of this "
+                  "type with internalize_spatial_softmax = False.")
+            self.n_output_heads = 2
+            self.learned_beta = learned_beta
+            self.initial_beta = initial_beta
+        else:
+            self.n_output_heads = 1
+            self.learned_beta = False
+        assert isinstance(n_stages, int), \
+            'Expected "n_stages" to be an integer, but it is {}.'.format(type(n_stages))
+        assert 0 < n_stages and n_stages <= 6, \
+            "DreamHourglassMultiStage can only be constructed with 1 to 6 stages at this time."
+        self.num_stages = n_stages
+        for s in range(1, n_stages + 1):
+            n_in = n_image_input_channels if s == 1 else n_image_input_channels + n_keypoints
+            setattr(self, "stage%d" % s,
+                    DreamHourglass(n_keypoints, n_in, internalize_spatial_softmax, learned_beta, initial_beta,
+                                   skip_connections=skip_connections, deconv_decoder=deconv_decoder,
+                                   full_output=full_output))
+
+    input_normalization = _PlanModule.input_normalization
+
+    def forward(self, x, verbose=False):
+        stage1 = self.stage1
+        if x.is_cuda and x.dtype == torch.uint8:
+            stage1.input_normalization = self.input_normalization
+            x = stage1._check_input(x)                       # raw frames -> normalised fp32 NCHW, once for all stages
+        outputs = []
+        y = stage1(x)[0]                                     # "just keeping belief maps for now" (:477)
+        outputs.append(y)
+        for s in range(2, self.num_stages + 1):
+            if self.deconv_decoder or self.full_output:
+                y_up = y
+            else:
+                y_up = nn.functional.interpolate(y, scale_factor=4)
+            y = getattr(self, "stage%d" % s)(torch.cat([x, y_up], dim=1))[0]
+            outputs.append(y)
         return outputs
 
 

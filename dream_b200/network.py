@@ -211,13 +211,16 @@ class DreamNetwork:
             elif "full_output" in arch:
                 vgg_kwargs["deconv_decoder"] = arch["deconv_decoder"]
                 vgg_kwargs["full_output"] = True
+                if "n_stages" in arch:
+                    # like the reference (network.py:232-235) the stage count is only forwarded together with
+                    # "full_output"; otherwise DreamHourglassMultiStage's default (2) applies
+                    vgg_kwargs["n_stages"] = arch["n_stages"]
             if "skip_connections" in arch:
                 vgg_kwargs["skip_connections"] = arch["skip_connections"]
             if "n_stages" in arch:
-                raise NotImplementedError(
-                    "DreamHourglassMultiStage (architecture.n_stages, dream/models.py:350-553) is not built "
-                    "in dream_b200 yet; no shipped arch config uses it.")
-            net = models.DreamHourglass(self.n_keypoints, **vgg_kwargs)
+                net = models.DreamHourglassMultiStage(self.n_keypoints, **vgg_kwargs)
+            else:
+                net = models.DreamHourglass(self.n_keypoints, **vgg_kwargs)
         elif self.architecture_type == "resnet":
             assert arch["output_heads"] == ["belief_maps"]
             resnet_kwargs = {}
@@ -226,6 +229,10 @@ class DreamNetwork:
             net = models.ResnetSimple(self.n_keypoints, **resnet_kwargs)
         else:
             assert False, 'Network architecture type "{}" not defined.'.format(self.architecture_type)
+        if self.image_normalization:
+            # lets the model take raw uint8 [B,H,W,3] frames and apply the dataset's ToTensor + Normalize on device
+            net.input_normalization = (tuple(float(v) for v in self.image_normalization["mean"]),
+                                       tuple(float(v) for v in self.image_normalization["stdev"]))
         self.model = models.DataParallelShim(net).to(self.device)
 
         loss_type = arch["loss"]["type"]
@@ -268,6 +275,10 @@ class DreamNetwork:
         return loss
 
     def loss(self, network_input_heads, target):
+        if target.dim() == 3 and target.shape[-1] == 2:
+            # keypoints [B,K,2] in the output frame (the dataset's `keypoint_projections_output`) instead of
+            # rasterised maps: build the belief-map targets on the device (image_proc.py:866-910)
+            target = image_proc.belief_targets_device(target, self.trained_net_output_resolution())
         network_output_heads = self.model(network_input_heads[0])
         if self.network_config["architecture"]["output_heads"] == ["belief_maps"]:
             if "n_stages" in self.network_config["architecture"]:

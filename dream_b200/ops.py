@@ -6,6 +6,7 @@ current CUDA stream to libdreamb200.so.  Activations are NHWC fp16 (`[B,H,W,C]`,
 import ctypes as C
 import os
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -104,10 +105,25 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
     return y
 
 
-def first_conv3x3(x, w, bias):
-    """Fused first layer: fp32 NCHW [B,3,H,W] -> relu(conv3x3(x)+bias) as fp16 NHWC [B,H,W,64]."""
-    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+def _norm3(v):
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float32).reshape(-1), (3,)))
+    return a
+
+
+def first_conv3x3(x, w, bias, u8_norm=None):
+    """Fused first layer: fp32 NCHW [B,3,H,W] -> relu(conv3x3(x)+bias) as fp16 NHWC [B,H,W,64].
+    With `u8_norm=(mean, std)` x is a raw uint8 [B,H,W,3] batch, normalised while it is gathered."""
     assert tuple(w.shape) == (1, 64, 64) and w.dtype == torch.float16 and bias.numel() >= 64
+    if u8_norm is not None:
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.shape[3] == 3
+        B, H, W_, _ = x.shape
+        mean, std = _norm3(u8_norm[0]), _norm3(u8_norm[1])
+        y = torch.empty((B, H, W_, 64), dtype=torch.float16, device=x.device)
+        check(lib().dreamb200_first_conv3x3_u8(_ptr(x), mean.ctypes.data_as(C.c_void_p),
+                                               std.ctypes.data_as(C.c_void_p), _ptr(w), _ptr(bias), _ptr(y),
+                                               B, H, W_, _stream()), "dreamb200_first_conv3x3_u8")
+        return y
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
     B, _, H, W_ = x.shape
     y = torch.empty((B, H, W_, 64), dtype=torch.float16, device=x.device)
     e0 = e1 = None

@@ -79,6 +79,22 @@ int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream);
    x fp32 NCHW [B,3,H,W], w fp16 [1][64][64] (k=(r*3+s)*3+c, zero padded), bias fp32 [64] -> y fp16 NHWC [B,H,W,64] */
 int dreamb200_first_conv3x3(const float* x, const void* w, const float* bias, void* y, int B, int H, int W,
                             void* stream);
+/* the same layer fed with raw uint8 frames [B,H,W,3] (PIL / decoder layout): the dataset's
+ * ToTensor + Normalize (dream/datasets.py:60-75,177-179) is applied while gathering, with the same fp32
+ * operations ((u/255 - mean)/std), so the result is bit-identical to dreamb200_first_conv3x3 on the host-normalised
+ * tensor.  mean3 / std3: host pointers to 3 floats (config key image_normalization). */
+int dreamb200_first_conv3x3_u8(const void* x_u8, const float* mean3, const float* std3, const void* w,
+                               const float* bias, void* y, int B, int H, int W, void* stream);
+/* uint8 [B,H,W,3] -> fp32 NCHW [B,3,H,W] = Normalize(mean,std)(ToTensor(frame)), bit-exact
+ * (dream/datasets.py:60-75,177-179); mean3 / std3 host pointers */
+int dreamb200_normalize_u8(const void* x_u8_nhwc, float* y_nchw, int B, int H, int W, const float* mean3,
+                           const float* std3, void* stream);
+/* training targets (dream/image_proc.py:866-910 create_belief_map): pts fp32 [n_maps,2] (x,y) device pointer;
+ * out fp32 [n_maps,h,w]; a (2*window_radius+1)^2 stamp table[(dx^2+dy^2)] (host pointer, 2*radius^2+1 floats =
+ * float32(exp(-d2/(2 sigma^2))) computed by the caller in fp64) around the truncated integer centre, only when
+ * the window lies strictly inside the frame (u-r>=0, u+r+1<w, ...); zeros elsewhere. */
+int dreamb200_belief_targets(const float* pts, int n_maps, int h, int w, int window_radius, const float* table,
+                             float* out, void* stream);
 /* x fp32 NCHW [B,3,H,W] -> out fp16 NHWC [B,Ho,Wo,Kpad]; k=(r*S+s)*3+c, zero padded */
 int dreamb200_im2col_first(const float* x, void* out, int B, int H, int W,
                            int R, int S, int stride, int pad, int Ho, int Wo, int Kpad, void* stream);

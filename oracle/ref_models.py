@@ -90,6 +90,39 @@ def vgg_forward(sd, x, deconv_decoder=False, full_output=False, skip_connections
     return out
 
 
+def multistage_forward(sd, x, n_stages=2, deconv_decoder=False, full_output=False, skip_connections=False,
+                       prefix="module."):
+    """DreamHourglassMultiStage.forward (models.py:473-553): returns [y1, ..., yS]; stage s>1 sees
+    cat(x, previous belief maps), the latter nearest-upsampled x4 unless the stages already output at the input
+    resolution (:483-491)."""
+    outs = []
+    y = None
+    for s in range(1, n_stages + 1):
+        if s == 1:
+            xin = x
+        else:
+            y_up = y if (deconv_decoder or full_output) else F.interpolate(y, scale_factor=4)
+            xin = torch.cat([x, y_up], dim=1)
+        y = vgg_forward(sd, xin, deconv_decoder=deconv_decoder, full_output=full_output,
+                        skip_connections=skip_connections, prefix="%sstage%d." % (prefix, s))
+        outs.append(y)
+    return outs
+
+
+def multistage_state_dict(n_keypoints, n_stages, gains, deconv_decoder=False, full_output=False, seed=0,
+                          mode="default", prefix="module."):
+    """Synthetic weights for DreamHourglassMultiStage: stage s is synth_state_dict of a DreamHourglass with
+    3 (s=1) or 3+K input channels, seed+s, head gain gains[s-1], re-keyed to `stage<s>.*` (models.py:396-470)."""
+    sd = {}
+    for s in range(1, n_stages + 1):
+        shapes = vgg_state_shapes(n_keypoints, deconv_decoder=deconv_decoder, full_output=full_output,
+                                  prefix="module.", n_in=3 if s == 1 else 3 + n_keypoints)
+        one = synth_state_dict(shapes, seed=seed + s, out_gain=float(gains[s - 1]), mode=mode)
+        for k, v in one.items():
+            sd["%sstage%d.%s" % (prefix, s, k[len("module."):])] = v
+    return sd
+
+
 def _bn(sd, key, x, training, momentum=0.1):
     return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"],
                         sd[key + ".bias"], training=training, momentum=momentum, eps=1e-5)

@@ -1,0 +1,120 @@
+"""GPU: DreamHourglassMultiStage (dream/models.py:350-553) against the reference's
+golden outputs (tests/golden/net_ms*.npz, oracle/make_golden_multistage.py) and the oracle restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models
+
+pytestmark = pytest.mark.gpu
+
+BELIEF_TOL = 1e-3
+CASES = [("ms2", dict(n_stages=2)), ("ms3_full", dict(n_stages=3, full_output=True))]
+
+
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _build(kw, gains):
+    from dream_b200 import models
+    S = kw["n_stages"]
+    sd = ref_models.multistage_state_dict(7, S, gains, full_output=kw.get("full_output", False), prefix="")
+    net = models.DreamHourglassMultiStage(7, internalize_spatial_softmax=False, **kw)
+    assert list(net.state_dict().keys()) == list(sd.keys())            # reference key names and order
+    net.load_state_dict(sd)
+    return net.cuda(), sd
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_multistage_forward_matches_reference_golden(name, kw, golden_dir, built_lib):
+    g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+    net, _ = _build(kw, g["gains"])
+    net.eval()
+    with torch.no_grad():
+        outs = net(torch.from_numpy(g["x"]).cuda())
+    assert len(outs) == kw["n_stages"]
+    for s, y in enumerate(outs):
+        ref = g["y%d" % (s + 1)]
+        assert tuple(y.shape) == ref.shape
+        err = np.abs(y.cpu().numpy() - ref).max()
+        assert err <= BELIEF_TOL * max(1.0, np.abs(ref).max()), (s, err)
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_multistage_gradients_match_oracle_and_golden(name, kw, golden_dir, built_lib):
+    """Multi-stage loss (network.py:345-352) and its gradients; the gates are those of
+    test_hourglass_gradients_match_oracle_and_golden (loss 1e-3; direction / norm of every parameter gradient),
+    and the stage-1 parameters only get the right gradient if each later stage hands back d(loss)/d(input)."""
+    g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+    S = kw["n_stages"]
+    net, sd = _build(kw, g["gains"])
+    x, tg = torch.from_numpy(g["x"]), torch.from_numpy(g["target"])
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_outs = ref_models.multistage_forward(ref_sd, x, prefix="", **kw)
+    ref_loss = torch.nn.MSELoss()(torch.stack(ref_outs), tg.unsqueeze(0).expand([S] + [-1] * tg.dim()))
+    ref_loss.backward()
+    assert abs(ref_loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+
+    net.train()
+    outs = net(x.cuda())
+    loss = torch.nn.MSELoss()(torch.stack(outs), tg.cuda().unsqueeze(0).expand([S] + [-1] * tg.dim()))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * ref_loss.item()
+    for pname, p in net.named_parameters():
+        assert p.grad is not None, pname
+        got, ref = p.grad.cpu(), ref_sd[pname].grad
+        assert _cos(got, ref) >= 0.985, (pname, _cos(got, ref))
+        assert abs(float(got.norm() / ref.norm()) - 1.0) <= 0.04, (pname, float(got.norm() / ref.norm()))
+    for key in g.files:
+        if key.startswith("grad::"):
+            ref = torch.from_numpy(g[key])
+            got = dict(net.named_parameters())[key[6:]].grad.cpu()[:ref.shape[0]]
+            assert _cos(got, ref) >= 0.985, key
+
+
+def test_stage_input_gradient_teacher_forced(built_lib):
+    """d(loss)/d(input) of a 10-channel stage (image + 7 belief maps) vs torch autograd of the same first layer
+    on the same fp16 operands: checks the data-gradient path that only the multi-stage network uses."""
+    import torch.nn.functional as F
+    from dream_b200 import models
+    torch.manual_seed(0)
+    net = models.DreamHourglass(7, n_image_input_channels=10, internalize_spatial_softmax=False).cuda().train()
+    x = (torch.rand((2, 10, 32, 48), device="cuda") * 2 - 1).requires_grad_(True)
+    out = net(x)[0]
+    (out * torch.randn_like(out)).sum().backward()
+    assert x.grad is not None and tuple(x.grad.shape) == tuple(x.shape)
+    # finite-difference-free check: the input gradient must equal conv_transpose of the first layer's dY, which we
+    # recover from the weight gradient identity  <dW, W> = <dY, conv(x) - bias> = <dX, x>  (linearity of the layer)
+    w = net.layer_0_1_down._modules["0"].weight
+    lhs = float((w.grad * w.detach()).sum())
+    rhs = float((x.grad * x.detach()).sum())
+    assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), abs(rhs), 1e-6), (lhs, rhs)
+
+
+def test_facade_multistage_config(built_lib):
+    """architecture.n_stages builds DreamHourglassMultiStage; like the reference (network.py:232-235) the count is
+    only forwarded together with "full_output" -- otherwise the constructor default of 2 applies."""
+    from conftest import panda_config
+    from dream_b200 import models, network
+    cfg = panda_config("vgg", n_stages=3)
+    cfg["training"]["config"]["net_input_resolution"] = [64, 48]
+    net = network.create_network_from_config_data(cfg)
+    assert isinstance(net.model.module, models.DreamHourglassMultiStage) and net.model.module.num_stages == 2
+    assert net.trained_net_output_resolution() == (16, 12)
+    net.enable_evaluation()
+    x = torch.rand((2, 3, 48, 64), device="cuda") * 2 - 1
+    with torch.no_grad():
+        belief, kps = net.inference(x)
+    assert tuple(belief.shape) == (2, 7, 12, 16) and tuple(kps.shape) == (2, 7, 2)
+    net.enable_training()
+    l0 = net.train([x], torch.zeros((2, 7, 12, 16), device="cuda")).item()
+    for _ in range(3):
+        l1 = net.train([x], torch.zeros((2, 7, 12, 16), device="cuda")).item()
+    assert np.isfinite(l1) and l1 < l0
+    cfg3 = panda_config("vgg", n_stages=3, full_output=True, deconv_decoder=False)
+    cfg3["training"]["config"]["net_input_resolution"] = [32, 32]
+    net3 = network.create_network_from_config_data(cfg3)
+    assert net3.model.module.num_stages == 3 and net3.trained_net_output_resolution() == (32, 32)

@@ -143,3 +143,30 @@ def test_yaml_omap_loading(tmp_path):
     out = tmp_path / "out.yaml"
     network.dump_yaml_config(cfg, str(out))
     assert network.load_yaml_config(str(out))["architecture"]["input_heads"] == ["image_rgb"]
+
+
+# ------------------------------------------------------------------------------------------------
+# batched post-loop of analyze_ndds_dataset vs the per-sample restatement
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preproc,raw_res,net_in", [("shrink-and-crop", (640, 480), (400, 400)),
+                                                    ("resize", (640, 480), (400, 400)),
+                                                    ("none", (400, 400), (400, 400)),
+                                                    ("shrink-and-crop", (480, 640), (400, 400))])
+def test_batched_analysis_matches_sample_loop(preproc, raw_res, net_in):
+    from dream_b200 import analysis
+    from oracle import ref_analysis
+    rng = np.random.default_rng(7)
+    B, K = 33, 7
+    net_out = (net_in[0] // 4, net_in[1] // 4)
+    kps = rng.uniform(0, net_out[0], size=(B, K, 2)).astype(np.float32)
+    kps[rng.random((B, K)) < 0.2] = -999.999                      # undetected
+    kps[5] = -999.999                                              # a frame with no detection at all
+    gt = rng.uniform(-60, max(raw_res) + 60, size=(B, K, 2))       # some out of frame
+    gt[7, :, 0] = -5.0                                             # a frame with no in-frame ground truth
+    gt[9, 0] = (0.0, 0.0); gt[9, 1] = (raw_res[0], raw_res[1])     # inclusive bounds
+    det, metric = analysis.analyze_batch(kps, gt, net_out, net_in, raw_res, preproc)
+    det_ref, metric_ref = ref_analysis.sample_loop(kps, gt, net_out, net_in, raw_res, preproc)
+    assert det.shape == (B, K, 2) and det.dtype == np.float64
+    assert np.array_equal(det, det_ref)                            # same float64 operations, same order
+    assert np.array_equal(metric, metric_ref)
+    assert metric[5] == 999.999 and metric[7] == 999.999

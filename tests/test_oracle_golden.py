@@ -158,3 +158,73 @@ def test_softargmax_restatement_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "softargmax.npz"))
     xy = ref_peaks.soft_argmax(g["maps"], g["beta"]).numpy()
     assert np.abs(xy - g["xy"]).max() <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side fixtures generated from the reference's image_proc / torchvision
+# ------------------------------------------------------------------------------------------------
+def test_input_oracle_matches_reference_fixtures(golden_dir):
+    from oracle import ref_input
+    GOLD = golden_dir
+    g = np.load(os.path.join(GOLD, "normalize.npz"))
+    for tag in ("half", "imagenet"):
+        x = ref_input.normalize_u8(g["img"], g[tag + "::mean"], g[tag + "::std"])
+        assert np.array_equal(x, g[tag + "::x"]), tag
+    t = np.load(os.path.join(GOLD, "targets.npz"))
+    ref = ref_input.create_belief_map((100, 100), t["pts"])
+    assert np.array_equal(ref.astype(np.float32), t["tgt"]) and ref.sum() == float(t["tgt64_sum"])
+    assert np.array_equal(ref_input.create_belief_map((208, 160), t["pts2"]).astype(np.float32), t["tgt2"])
+    # the product's vectorised host version is the same function
+    from dream_b200 import image_proc
+    assert np.array_equal(image_proc.create_belief_map((100, 100), t["pts"]), ref)
+    # window edge cases of the fixture: (4,4) and (94,94) stamp, (3.99,50), (95,50), (50.5,94.999), sentinel do not
+    sums = t["tgt"].reshape(len(t["pts"]), -1).sum(1)
+    assert sums[0] > 0 and sums[2] > 0 and sums[1] == 0 and sums[3] == 0 and sums[5] == 0
+
+
+def test_frame_conversions_match_reference_fixture(golden_dir):
+    GOLD = golden_dir
+    from dream_b200 import analysis, image_proc
+    from oracle import ref_analysis
+    g = np.load(os.path.join(GOLD, "frames.npz"))
+    n = len([k for k in g.files if k.endswith("::meta")])
+    assert n == 5
+    for i in range(n):
+        preproc, rw, rh, nw, nh = g["case%d::meta" % i]
+        raw, net_in = (int(rw), int(rh)), (int(nw), int(nh))
+        net_out = (net_in[0] // 4, net_in[1] // 4)
+        kps = g["case%d::kps" % i]
+        netin = image_proc.convert_keypoints_to_netin_from_netout(kps, net_out, net_in)
+        assert np.array_equal(netin, g["case%d::netin" % i])
+        raw_kp = image_proc.convert_keypoints_to_raw_from_netin(netin, net_in, raw, preproc)
+        assert np.array_equal(raw_kp, g["case%d::raw" % i])
+        back = image_proc.convert_keypoints_to_netin_from_raw(raw_kp, raw, net_in, preproc)
+        assert np.array_equal(back, g["case%d::back" % i])
+        assert np.array_equal(analysis.detected_keypoints_raw(kps[None], net_out, net_in, raw, preproc)[0],
+                              g["case%d::raw" % i])
+        det, _ = ref_analysis.sample_loop(kps[None], np.zeros((1, len(kps), 2)), net_out, net_in, raw, preproc)
+        assert np.array_equal(det[0], g["case%d::raw" % i])
+
+
+@pytest.mark.parametrize("name,kw", [("ms2", dict(n_stages=2)), ("ms3_full", dict(n_stages=3, full_output=True))])
+def test_multistage_restatement_matches_reference(name, kw, golden_dir):
+    """DreamHourglassMultiStage (models.py:350-553): every stage's belief maps, the multi-stage loss of
+    network.py:345-352 and gradients (incl. stage-1 parameters reached through later stages)."""
+    g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+    S = kw["n_stages"]
+    sd = ref_models.multistage_state_dict(7, S, g["gains"], full_output=kw.get("full_output", False), prefix="")
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = torch.from_numpy(g["x"])
+    outs = ref_models.multistage_forward(sd, x, prefix="", **kw)
+    assert len(outs) == S
+    for s, y in enumerate(outs):
+        assert np.abs(y.detach().numpy() - g["y%d" % (s + 1)]).max() <= 1e-5
+    tg = torch.from_numpy(g["target"])
+    loss = torch.nn.MSELoss()(torch.stack(outs), tg.unsqueeze(0).expand([S] + [-1] * tg.dim()))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    loss.backward()
+    for key in g.files:
+        if key.startswith("grad::"):
+            ref = g[key]
+            got = sd[key[6:]].grad.numpy()[:ref.shape[0]]
+            assert np.abs(got - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-12), key
