@@ -236,6 +236,19 @@ int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint6
   return 0;
 }
 
+// Un-swizzled map over a plain fp32 / uint8 tensor (input staging of first_conv.cu). kind: 0 = fp32, 1 = uint8.
+int make_tensor_map_plain(CUtensorMap* tm, int kind, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  uint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank,
+                   const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
 // Pick the output patch (tw x th <= 128 pixels) that wastes the fewest accumulator rows.
 // `even` forces even patch sides (needed when a 2x2 pool is fused on top of the patch).
 static double choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, int* th_out) {
