@@ -26,6 +26,7 @@ class ConvDesc(C.Structure):
         ("relu", C.c_int32),
         ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p), ("y_pool", C.c_void_p),
         ("absmax", C.c_void_p),
+        ("gate", C.c_void_p), ("out_scale", C.c_void_p),
     ]
 
 
@@ -68,7 +69,7 @@ _PROTOS = {
     "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dreamb200_scale_mask_bias_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_absmax_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
-    "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
     "dreamb200_upsample2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_bias_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_softargmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 +

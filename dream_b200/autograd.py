@@ -23,6 +23,10 @@ from . import models, ops
 # (key, dY as fed to the layer's kernels [fp16, already scaled+masked], cumulative scale [1-elem tensor],
 #  layer input [fp16 NHWC], dX produced [fp16 NHWC or None]).  None = no capture, no cost.
 DEBUG_CAPTURE = None
+# Fold ReLU masks / re-scaling into the gradient-producing kernels (see backward).  DREAMB200_FUSE_GATES=0 restores
+# the separate pass over every dY (kept for A/B timing).
+import os as _os
+_FUSE_GATES = _os.environ.get("DREAMB200_FUSE_GATES", "1") != "0"
 
 
 def _dgrad_pack(weight, cin_pad, cout_pad):
@@ -129,22 +133,45 @@ class _HourglassTrainFn(torch.autograd.Function):
         grads = {}
         go = grad_out.contiguous().float()
         # fp16 gradients: every layer's dY is re-scaled by a power of two (computed on the device, no host
-        # sync) so that max|dY| sits near 2^8; `cum` is the product of all factors applied so far and the
+        # sync) so that max|dY| stays near 2^8; `cum` is the product of all factors applied so far and the
         # fp32 parameter gradients are divided by it.  Without this the trunk's dY drift into fp16
         # subnormals (gradient norms shrink ~400x from the head to the first layer).
+        #
+        # Where a layer's input is directly the ReLU output of the previous conv (or its 2x2 max pool), that ReLU's
+        # mask and the re-scaling are applied by the kernel that PRODUCES the gradient -- the data-gradient conv's
+        # epilogue (`gate`, `out_scale`) or the pool backward (`relu_gate`) -- instead of a separate pass over dY;
+        # `ready` says the current g already went through them.  The scale then lags one layer behind (it is
+        # derived from max|dY| of the layer above): adjacent layers' gradient magnitudes differ by far less than
+        # the 2^7 of headroom on either side.
+        def pow2_scale(amax):
+            return torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
+
         amax = go.abs().amax().clamp_min(1e-30)
         cum = torch.exp2(torch.floor(torch.log2(256.0 / amax))).reshape(1)
         g = ops.nchw_to_nhwc_f16((go * cum).contiguous(), 64)           # [B,h,w,64], channels >= K are zero
         amax = ops.absmax(g)            # later layers get max|dY| for free from the producing data-gradient kernel
+        ready = False
         stash = {}                      # skip connections: gradient of the skip addend, with the scale it carries
         gx = None
-        for kind, key, xin, yout in reversed(tape):
+        fuse = _FUSE_GATES
+
+        def producer_of(i):
+            """(gate tensor or None, fusable) for the gradient flowing INTO tape entry i's output."""
+            kind, key, _xin, yout = tape[i]
+            if kind in ("conv", "deconv", "first"):
+                pc = P["first"] if kind == "first" else P[key]
+                return (yout if pc.relu else None), True
+            return None, False
+
+        for i in range(len(tape) - 1, -1, -1):
+            kind, key, xin, yout = tape[i]
             if kind == "input":
                 if ctx.needs_input_grad[1]:
                     gx = ops.nhwc_to_nchw_f32(g, ctx.n_in) * (1.0 / cum)
                 continue
             if kind == "add":
                 stash[key] = (g.clone(), cum.clone())
+                ready = False
                 continue
             if kind == "mark":
                 if key not in stash:            # this tensor was not used as a skip by the configured decoder
@@ -153,60 +180,72 @@ class _HourglassTrainFn(torch.autograd.Function):
                 ops.scale_mask_(sg, None, cum / scum)           # bring it to the current loss scale, then accumulate
                 ops.add_(g, sg)
                 amax = ops.absmax(g)
+                ready = False
                 continue
-            if kind in ("conv", "head", "first"):
+            if kind in ("conv", "head", "first", "deconv"):
                 node = models._node_for(model, key)
                 pc = P["first"] if kind == "first" else P[key]
-                f = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
-                cum = cum * f
+                deconv = kind == "deconv"
+                if deconv:
+                    cin, cout = node.weight.shape[0], node.weight.shape[1]      # ConvTranspose2d: [Cin, Cout, 3, 3]
+                else:
+                    cout, cin = node.weight.shape[0], node.weight.shape[1]
+                if ready:
+                    db = ops.bias_grad(g) if node.bias is not None else None    # mask + scale already applied
+                else:
+                    # ReLU mask + re-scaling + bias gradient in one pass over dY
+                    f = pow2_scale(amax)
+                    cum = cum * f
+                    amax = amax * f
+                    db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
                 inv = 1.0 / cum
-                cout, cin = node.weight.shape[0], node.weight.shape[1]
-                # ReLU mask + re-scaling + bias gradient in one pass over dY
-                db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
                 if node.bias is not None:
                     grads[key + ".bias"] = db[:cout] * inv
                 if kind == "first":
                     dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]                   # [co, (r,s,c)]
                     grads[key + ".weight"] = (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                    if DEBUG_CAPTURE is not None:
+                        DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None, None, None))
                     g = None                                                           # the image needs no grad
+                    continue
+                # what sits below this layer's input decides how its data gradient leaves the kernel
+                gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)
+                below_is_pool = fuse and i > 0 and tape[i - 1][0] == "pool"
+                f_out = pow2_scale(amax) if (below_is_conv or below_is_pool) else None
+                g_in, cum_in = g, cum
+                amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
+                B, H, W, _ = xin.shape
+                if deconv:
+                    # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
+                    dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
+                    grads[key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
+                    # dX[p] = sum_taps W[:, :, tap] dY[2p + tap-1]: a stride-2 3x3 conv over dY
+                    rs = [(r, s_) for r in range(3) for s_ in range(3)]
+                    wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
+                    g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2, absmax=amax,
+                                      gate=gate if below_is_conv else None, out_scale=f_out)
                 else:
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3)[:, :cout, :cin]               # [9, co, ci]
                     grads[key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
-                    B, H, W, _ = xin.shape
-                    g_in = g
-                    amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
-                    g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax)
-                    if DEBUG_CAPTURE is not None:
-                        DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))   # g is re-scaled in place later
-                if kind == "first" and DEBUG_CAPTURE is not None:
-                    DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None))
-            elif kind == "deconv":
-                node = models._node_for(model, key)
-                pc = P[key]
-                f = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
-                cum = cum * f
-                inv = 1.0 / cum
-                cin, cout = node.weight.shape[0], node.weight.shape[1]          # ConvTranspose2d: [Cin, Cout, 3, 3]
-                db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
-                if node.bias is not None:
-                    grads[key + ".bias"] = db[:cout] * inv
-                # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
-                dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
-                grads[key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
-                # dX[p] = sum_taps W[:, :, tap] dY[2p + tap-1]: a stride-2 3x3 conv over dY
-                rs = [(r, s_) for r in range(3) for s_ in range(3)]
-                wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
-                B, H, W, _ = xin.shape
-                g_in = g
-                amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
-                g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2, absmax=amax)
+                    g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax,
+                                      gate=gate if below_is_conv else None, out_scale=f_out)
+                if f_out is not None:
+                    cum = cum * f_out
+                ready = below_is_conv            # (below a pool the ReLU gate is applied by the pool backward)
                 if DEBUG_CAPTURE is not None:
-                    DEBUG_CAPTURE.append((key, g_in, cum.clone(), xin, g.clone()))
+                    # (key, dY fed to the kernels, its scale, layer input, dX produced, ReLU gate folded into dX, dX's scale)
+                    DEBUG_CAPTURE.append((key, g_in, cum_in.clone(), xin, g.clone(),
+                                          gate if below_is_conv else None, cum.clone()))
             elif kind == "pool":
-                g = ops.maxpool2_bwd(xin, g)
+                gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)
+                g = ops.maxpool2_bwd(xin, g, relu_gate=below_is_conv and gate is not None)
+                # the re-scaling for the layer below was folded into the data-gradient conv above the pool (`f_out`),
+                # the pool backward adds that layer's ReLU gate; max|g| does not grow, so `amax` stays a bound
+                ready = below_is_conv
             elif kind == "up":
                 g = ops.upsample2_bwd(g)        # sums 4 values: the stale `amax` can under-estimate by <= 4x (256x headroom)
+                ready = False
         ctx.tape = None
         return (None, gx) + tuple(grads.get(n) for n in ctx.param_names)
 

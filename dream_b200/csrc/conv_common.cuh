@@ -28,6 +28,8 @@ struct ConvParams {
   // division-free tile decode: q = (x * magic) >> 40 is exact for x < 2^24, divisor < 2^16 (host: 2^40/d + 1)
   unsigned long long mg_n, mg_x, mg_y;
   float* absmax;    // optional: running max |output| (bits of a non-negative float), see dreamb200_conv_desc
+  const __half* gate;      // optional ReLU gate of the backward pass: output zeroed where gate <= 0
+  const float* out_scale;  // optional device scalar multiplied into every output
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
@@ -87,6 +89,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   if (p.residual != nullptr && valid) res_row = p.residual + row_off;
   if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
   if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
+  const __half* gate_row = (p.gate != nullptr && valid) ? p.gate + row_off : nullptr;
+  const float out_scale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.0f;
   const bool shfl_pool = p.pool && (p.tw == 8 || p.tw == 16);
   const bool write_full = !p.pool || p.store_full || !shfl_pool;
 #pragma unroll 1
@@ -135,6 +139,24 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       if (p.relu) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+      }
+      if (p.gate != nullptr) {
+        // data gradient leaving through the previous layer's ReLU: keep it where that layer's output was > 0
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 gv = make_uint4(0u, 0u, 0u, 0u);
+          if (gate_row != nullptr) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + c * 64 + h * 32 + i));
+          const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 gf = __half22float2(gh[j]);
+            f[i + 2 * j] = gf.x > 0.0f ? f[i + 2 * j] * out_scale : 0.0f;
+            f[i + 2 * j + 1] = gf.y > 0.0f ? f[i + 2 * j + 1] * out_scale : 0.0f;
+          }
+        }
+      } else if (p.out_scale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] *= out_scale;
       }
       if (y32_row != nullptr) {
 #pragma unroll

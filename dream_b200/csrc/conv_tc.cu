@@ -297,6 +297,8 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
                  p.tiles_y < 65536 && p.n_tiles < 65536,
              "conv: too many tiles for one launch (%d x %d x %d x %d)", p.tiles_x, p.tiles_y, p.n_tiles, d->B);
   p.absmax = d->absmax;
+  p.gate = reinterpret_cast<const __half*>(d->gate);
+  p.out_scale = d->out_scale;
   p.mg_n = div_magic(p.n_tiles);
   p.mg_x = div_magic(p.tiles_x);
   p.mg_y = div_magic(p.tiles_y);

@@ -476,31 +476,33 @@ __global__ void absmax_kernel(const uint4* __restrict__ x, long long n8, int* __
   }
 }
 
-// 2x2/s2 max-pool backward (floor mode): gradient goes to the first maximum of each window (ATen order)
+// 2x2/s2 max-pool backward (floor mode): gradient goes to the first maximum of each window (ATen order).
+// One thread per window and 8 channels: reads the 4 inputs + dy once, writes the 4 gradients.  With `gate` the pooled
+// tensor is a ReLU output and the gradient continues through that ReLU: a window whose maximum is 0 passes nothing
+// (fuses the mask pass of the preceding conv layer, autograd of models.py:589 + the trunk's nn.ReLU).
 __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
-                                    int B, int H, int W, int C8, int Ho, int Wo) {
-  const long long total = (long long)B * H * W * C8;
+                                    int B, int H, int W, int C8, int Ho, int Wo, int gate) {
+  const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;      // windows incl. the partial ones of an odd edge (all-zero grad)
+  const long long total = (long long)B * Hc * Wc * C8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C8);
     long long pix = idx / C8;
-    const int ix = (int)(pix % W);
-    pix /= W;
-    const int iy = (int)(pix % H);
-    const int b = (int)(pix / H);
-    const int oy = iy >> 1, ox = ix >> 1;
-    uint4 out = make_uint4(0, 0, 0, 0);
+    const int ox = (int)(pix % Wc);
+    pix /= Wc;
+    const int oy = (int)(pix % Hc);
+    const int b = (int)(pix / Hc);
+    const size_t base = ((size_t)((size_t)b * H + 2 * oy) * W + 2 * ox) * C8 + c;
+    const size_t off[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
+    uint4 out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = make_uint4(0, 0, 0, 0);
     if (oy < Ho && ox < Wo) {
-      const size_t base = ((size_t)((size_t)b * H + 2 * oy) * W + 2 * ox) * C8 + c;
       uint4 v[4];
-      v[0] = __ldg(x + base);
-      v[1] = __ldg(x + base + C8);
-      v[2] = __ldg(x + base + (size_t)W * C8);
-      v[3] = __ldg(x + base + (size_t)W * C8 + C8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(x + base + off[k]);
       const uint4 g = __ldg(dy + ((size_t)((size_t)b * Ho + oy) * Wo + ox) * C8 + c);
-      const int me = (iy & 1) * 2 + (ix & 1);
       const __half* gh = reinterpret_cast<const __half*>(&g);
-      __half* oh = reinterpret_cast<__half*>(&out);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int arg = 0;
@@ -510,10 +512,18 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
           const float f = __half2float(reinterpret_cast<const __half*>(&v[k])[j]);
           if (f > best) { best = f; arg = k; }
         }
-        oh[j] = arg == me ? gh[j] : __float2half(0.0f);
+        if (!gate || best > 0.0f) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k == arg) reinterpret_cast<__half*>(&out[k])[j] = gh[j];
+        }
       }
     }
-    dx[idx] = out;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int iy = 2 * oy + (k >> 1), ix = 2 * ox + (k & 1);
+      if (iy < H && ix < W) dx[base + off[k]] = out[k];
+    }
   }
 }
 
@@ -867,12 +877,12 @@ extern "C" int dreamb200_absmax_f16(const void* x, long long n, float* out, void
 }
 
 extern "C" int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C,
-                                           void* stream) {
+                                           int relu_gate, void* stream) {
   DB_REQUIRE(x && dy && dx && C % 8 == 0, "maxpool2_bwd: bad arguments");
-  const long long total = (long long)B * H * W * (C / 8);
+  const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   maxpool2_bwd_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), B, H, W,
-      C / 8, H / 2, W / 2);
+      C / 8, H / 2, W / 2, relu_gate);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -32,7 +32,8 @@ def round_up(v, m):
 
 
 def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
-              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None, absmax=None):
+              y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None, absmax=None,
+              gate=None, out_scale=None):
     """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
 
     x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
@@ -84,6 +85,13 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
     if absmax is not None:          # 1-element fp32 cuda tensor (zeroed): receives max |y| of this launch
         assert absmax.dtype == torch.float32 and absmax.numel() == 1 and head_cout is None
         d.absmax = absmax.data_ptr()
+    if gate is not None:            # backward pass: zero the outputs where this fp16 tensor (a ReLU output) is <= 0
+        assert gate.dtype == torch.float16 and gate.is_contiguous() and tuple(gate.shape) == (B, Ho, Wo, Cout_pad)
+        assert head_cout is None and pool is None
+        d.gate = gate.data_ptr()
+    if out_scale is not None:       # 1-element fp32 cuda tensor multiplied into every output
+        assert out_scale.dtype == torch.float32 and out_scale.numel() == 1 and head_cout is None
+        d.out_scale = out_scale.data_ptr()
     for name, t in (("residual_f32", residual_f32), ("y_f32", y_f32)):
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, Ho, Wo, Cout_pad)
@@ -299,11 +307,12 @@ def absmax(x):
     return out
 
 
-def maxpool2_bwd(x, dy):
+def maxpool2_bwd(x, dy, relu_gate=False):
+    """Gradient of nn.MaxPool2d(2); with `relu_gate` x is a ReLU output and the gradient also passes that ReLU."""
     B, H, W_, Cc = x.shape
     dx = torch.empty_like(x)
-    check(lib().dreamb200_maxpool2_bwd_nhwc(_ptr(x), _ptr(dy), _ptr(dx), B, H, W_, Cc, _stream()),
-          "dreamb200_maxpool2_bwd_nhwc")
+    check(lib().dreamb200_maxpool2_bwd_nhwc(_ptr(x), _ptr(dy), _ptr(dx), B, H, W_, Cc, 1 if relu_gate else 0,
+                                            _stream()), "dreamb200_maxpool2_bwd_nhwc")
     return dx
 
 

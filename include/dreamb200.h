@@ -62,6 +62,12 @@ typedef struct dreamb200_conv_desc {
   /* when set: *absmax = max(*absmax, max |y|) over the fp16 outputs written by this launch (device float holding a
      non-negative value, zeroed by the caller) -- lets the backward pass pick the next layer's loss scale for free */
   float* absmax;
+  /* backward-pass epilogue (data gradient of layer l feeding the ReLU of layer l-1, autograd of models.py:761-827):
+     gate, fp16 NHWC [B,Ho,Wo,Cout_pad] or NULL: outputs where gate <= 0 are zeroed (the ReLU mask, taken from the
+     saved forward activation); out_scale, device pointer to one float or NULL: every output is multiplied by it
+     (power-of-two loss re-scaling chosen on the device).  Applied before `absmax`. */
+  const void* gate;
+  const float* out_scale;
 } dreamb200_conv_desc;
 
 /* fraction of the 128 accumulator rows a conv with this output size keeps busy, for the free tile
@@ -152,8 +158,10 @@ int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const float* scale, f
                                   void* stream);
 /* *out = max(*out, max|x|) over n fp16 values (out: device float, zeroed by the caller) */
 int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream);
-/* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C] */
-int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C].  relu_gate != 0: x is a
+ * ReLU output and the gradient continues through that ReLU (windows whose maximum is 0 pass nothing). */
+int dreamb200_maxpool2_bwd_nhwc(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int relu_gate,
+                                void* stream);
 /* autograd of nn.Upsample(scale_factor=2): dy [B,2H,2W,C] -> dx [B,H,W,C] */
 int dreamb200_upsample2_bwd_nhwc(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 /* db[c] += sum_rows dy[row][c]; dy fp16 [rows,C], C % 64 == 0 (caller zeroes db) */

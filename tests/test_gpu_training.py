@@ -57,6 +57,11 @@ def test_streaming_backward_kernels_match_torch(built_lib):
     yp.backward(dy.float())
     dx = ops.maxpool2_bwd(x, dy.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(dx.permute(0, 3, 1, 2).float(), xr.grad)
+    # ... fused with the ReLU in front of the pool: d/dx of max_pool2d(relu(x)), evaluated on y = relu(x)
+    xr.grad = None
+    F.max_pool2d(torch.relu(xr), 2).backward(dy.float())
+    dxg = ops.maxpool2_bwd(torch.relu(x), dy.permute(0, 2, 3, 1).contiguous(), relu_gate=True)
+    assert torch.equal(dxg.permute(0, 3, 1, 2).float(), xr.grad)
     # upsample backward
     xr.grad = None
     yu = F.interpolate(xr, scale_factor=2)
@@ -72,6 +77,29 @@ def test_streaming_backward_kernels_match_torch(built_lib):
     assert torch.equal(got.float(), ref_mask)
     db = ops.bias_grad(got)
     assert (db - ref_mask.sum(dim=(0, 1, 2))).abs().max() <= 1e-3 * ref_mask.abs().sum(dim=(0, 1, 2)).max()
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(2, 32, 48, 64, 64), (2, 25, 25, 256, 128), (1, 50, 50, 128, 256)])
+def test_conv_epilogue_gate_and_scale(B, H, W, Ci, Co, built_lib):
+    """`gate` / `out_scale` of dreamb200_conv_desc (the data-gradient epilogue): y = conv(x) * scale where gate > 0,
+    else 0, and absmax sees the gated, scaled values."""
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.randn((B, H, W, Ci), device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn((9, Co, Ci), device="cuda", generator=g) * (1.0 / (3 * Ci ** 0.5))).half()
+    gate = torch.relu(torch.randn((B, H, W, Co), device="cuda", generator=g)).half()
+    scale = torch.tensor([4.0], device="cuda")
+    plain = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W)
+    amax = torch.zeros((1,), dtype=torch.float32, device="cuda")
+    got = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, gate=gate, out_scale=scale, absmax=amax)
+    ref = (plain.float() * 4.0) * (gate > 0)
+    # a power-of-two scale commutes with the fp16 rounding except for results in the subnormal range (spacing 2^-24)
+    assert (got.float() - ref).abs().max().item() <= 4 * 2.0 ** -24
+    assert torch.equal(got.float() == 0, ref == 0) or bool(((got.float() == 0) | (ref.abs() <= 4 * 2.0 ** -24)).all())
+    assert torch.equal((got.float() != 0) & (gate <= 0), torch.zeros_like(gate, dtype=torch.bool))
+    assert abs(amax.item() - ref.abs().max().item()) <= 1e-6
+    only_scale = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, out_scale=scale)
+    assert (only_scale.float() - plain.float() * 4.0).abs().max().item() <= 4 * 2.0 ** -24
 
 
 def _cos(a, b):
@@ -149,7 +177,8 @@ def test_backward_kernels_layerwise_teacher_forced(arch, built_lib):
         autograd.DEBUG_CAPTURE = None
     params = dict(net.named_parameters())
     checked = 0
-    for key, g_in, cum, xin, dx in cap:
+    fused = 0
+    for key, g_in, cum, xin, dx, gate, dx_cum in cap:
         if g_in is None:
             continue
         w = params[key + ".weight"].detach()
@@ -167,10 +196,17 @@ def test_backward_kernels_layerwise_teacher_forced(arch, built_lib):
         y.backward(gy)
         assert _rel(params[key + ".weight"].grad, wr.grad) <= 3e-3, (key, "wgrad", _rel(params[key + ".weight"].grad, wr.grad))
         assert _rel(params[key + ".bias"].grad, br.grad) <= 3e-3, (key, "bias", _rel(params[key + ".bias"].grad, br.grad))
-        got_dx = dx[..., :cin].permute(0, 3, 1, 2).float() / cum
-        assert _rel(got_dx, xr.grad) <= 3e-3, (key, "dgrad", _rel(got_dx, xr.grad))
+        # the data gradient leaves the kernel already multiplied by the next loss-scale factor (dx_cum) and, where
+        # the layer below is a ReLU conv, gated by that layer's saved output
+        got_dx = dx[..., :cin].permute(0, 3, 1, 2).float() / dx_cum
+        ref_dx = xr.grad
+        if gate is not None:
+            ref_dx = ref_dx * (gate[..., :cin].permute(0, 3, 1, 2).float() > 0)
+            fused += 1
+        assert _rel(got_dx, ref_dx) <= 3e-3, (key, "dgrad", _rel(got_dx, ref_dx))
         checked += 1
     assert checked == (25 if arch == "vgg_f" else 22)
+    assert fused >= (14 if arch == "vgg_f" else 15), fused
 
 
 @pytest.mark.parametrize("kw", [dict(deconv_decoder=True, full_output=True), dict(skip_connections=True),
