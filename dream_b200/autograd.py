@@ -67,9 +67,11 @@ class _HourglassTrainFn(torch.autograd.Function):
             tape.append(("add", name, None, None))
             return out
 
+        pooled = None
         for bi, (block, idxs, _) in enumerate(models.VGG_TRUNK):
             if bi > 0:
-                y = ops.maxpool(t, 2, 2, 0)
+                y = pooled if pooled is not None else ops.maxpool(t, 2, 2, 0)
+                pooled = None
                 tape.append(("pool", None, t, y))
                 t = y
                 if sk:
@@ -79,7 +81,13 @@ class _HourglassTrainFn(torch.autograd.Function):
                 if block == "layer_0_1_down" and j == 0:
                     continue
                 key = "%s.%d" % (block, j)
-                y = models._run_conv(P[key], t)
+                pc = P[key]
+                if j == idxs[-1] and bi < len(models.VGG_TRUNK) - 1 and ops.pool_fusion_pays(t.shape[1], t.shape[2]):
+                    # nn.MaxPool2d(2) fused into this conv's epilogue; the tape needs the un-pooled tensor too
+                    y, pooled = ops.conv_taps(t, pc.w, pc.b, pc.taps, t.shape[1], t.shape[2], relu=pc.relu,
+                                              pool="both")
+                else:
+                    y = models._run_conv(pc, t)
                 tape.append(("conv", key, t, y))
                 t = y
             if sk and block == "layer_0_1_down":
@@ -143,12 +151,11 @@ class _HourglassTrainFn(torch.autograd.Function):
         # `ready` says the current g already went through them.  The scale then lags one layer behind (it is
         # derived from max|dY| of the layer above): adjacent layers' gradient magnitudes differ by far less than
         # the 2^7 of headroom on either side.
-        def pow2_scale(amax):
-            return torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 20)
-
-        amax = go.abs().amax().clamp_min(1e-30)
-        cum = torch.exp2(torch.floor(torch.log2(256.0 / amax))).reshape(1)
-        g = ops.nchw_to_nhwc_f16((go * cum).contiguous(), 64)           # [B,h,w,64], channels >= K are zero
+        # (`cum` is updated IN PLACE by ops.loss_scale_step; everything that needs an earlier value clones it)
+        amax = go.abs().amax().reshape(1)
+        cum = torch.ones((1,), dtype=torch.float32, device=go.device)
+        f, inv = ops.loss_scale_step(amax, cum)
+        g = ops.nchw_to_nhwc_f16((go * f).contiguous(), 64)             # [B,h,w,64], channels >= K are zero
         amax = ops.absmax(g)            # later layers get max|dY| for free from the producing data-gradient kernel
         ready = False
         stash = {}                      # skip connections: gradient of the skip addend, with the scale it carries
@@ -167,7 +174,7 @@ class _HourglassTrainFn(torch.autograd.Function):
             kind, key, xin, yout = tape[i]
             if kind == "input":
                 if ctx.needs_input_grad[1]:
-                    gx = ops.nhwc_to_nchw_f32(g, ctx.n_in) * (1.0 / cum)
+                    gx = ops.nhwc_to_nchw_f32(g, ctx.n_in) * inv
                 continue
             if kind == "add":
                 stash[key] = (g.clone(), cum.clone())
@@ -194,11 +201,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                     db = ops.bias_grad(g) if node.bias is not None else None    # mask + scale already applied
                 else:
                     # ReLU mask + re-scaling + bias gradient in one pass over dY
-                    f = pow2_scale(amax)
-                    cum = cum * f
-                    amax = amax * f
+                    f, inv = ops.loss_scale_step(amax, cum)
                     db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
-                inv = 1.0 / cum
                 if node.bias is not None:
                     grads[key + ".bias"] = db[:cout] * inv
                 if kind == "first":
@@ -211,14 +215,20 @@ class _HourglassTrainFn(torch.autograd.Function):
                 # what sits below this layer's input decides how its data gradient leaves the kernel
                 gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)
                 below_is_pool = fuse and i > 0 and tape[i - 1][0] == "pool"
-                f_out = pow2_scale(amax) if (below_is_conv or below_is_pool) else None
-                g_in, cum_in = g, cum
+                g_in = g
+                cum_in = cum.clone() if DEBUG_CAPTURE is not None else None
+                f_out = None
+                inv_here = inv
+                if ready and (below_is_conv or below_is_pool):
+                    # `amax` is the measured max of this (already gated) dY: choose the factor its data gradient
+                    # leaves with.  (After the unfused pass above dY was just normalised: factor 1.)
+                    f_out, inv = ops.loss_scale_step(amax, cum)
                 amax = torch.zeros((1,), dtype=torch.float32, device=g.device)
                 B, H, W, _ = xin.shape
                 if deconv:
                     # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
-                    grads[key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
+                    grads[key + ".weight"] = (dw * inv_here).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
                     # dX[p] = sum_taps W[:, :, tap] dY[2p + tap-1]: a stride-2 3x3 conv over dY
                     rs = [(r, s_) for r in range(3) for s_ in range(3)]
                     wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
@@ -226,16 +236,14 @@ class _HourglassTrainFn(torch.autograd.Function):
                                       gate=gate if below_is_conv else None, out_scale=f_out)
                 else:
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3)[:, :cout, :cin]               # [9, co, ci]
-                    grads[key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
+                    grads[key + ".weight"] = (dw * inv_here).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
                     g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax,
                                       gate=gate if below_is_conv else None, out_scale=f_out)
-                if f_out is not None:
-                    cum = cum * f_out
                 ready = below_is_conv            # (below a pool the ReLU gate is applied by the pool backward)
                 if DEBUG_CAPTURE is not None:
                     # (key, dY fed to the kernels, its scale, layer input, dX produced, ReLU gate folded into dX, dX's scale)
-                    DEBUG_CAPTURE.append((key, g_in, cum_in.clone(), xin, g.clone(),
+                    DEBUG_CAPTURE.append((key, g_in, cum_in, xin, g.clone(),
                                           gate if below_is_conv else None, cum.clone()))
             elif kind == "pool":
                 gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)

@@ -867,6 +867,28 @@ extern "C" int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const floa
   return 0;
 }
 
+// One step of the backward pass' loss re-scaling, entirely on the device: f = 2^floor(log2(target / max|dY|))
+// (clamped to 2^+-20), cum *= f, inv = 1 / cum.  Replaces ~10 single-element torch kernels per layer.
+__global__ void loss_scale_step_kernel(const float* __restrict__ amax, float* __restrict__ cum, float* __restrict__ f_out,
+                                       float* __restrict__ inv_out, float target) {
+  const float a = fmaxf(*amax, 1e-30f);
+  float f = exp2f(floorf(log2f(target / a)));
+  f = fminf(fmaxf(f, 9.5367431640625e-07f), 1048576.0f);
+  const float c = *cum * f;
+  *cum = c;
+  *f_out = f;
+  *inv_out = 1.0f / c;
+}
+
+extern "C" int dreamb200_loss_scale_step(const float* amax, float* cum, float* f_out, float* inv_out, float target,
+                                         void* stream) {
+  DB_REQUIRE(amax && cum && f_out && inv_out && target > 0.0f, "loss_scale_step: bad arguments");
+  loss_scale_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(amax, cum, f_out, inv_out, target);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 extern "C" int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream) {
   DB_REQUIRE(x && out && n > 0 && n % 8 == 0, "absmax: bad arguments");
   absmax_kernel<<<grid_cap(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), n / 8,

@@ -184,6 +184,24 @@ def _run_deconv(pc, x):
     return y
 
 
+class _LazyPlan(dict):
+    """Plan entries are packed on first use: a training step only touches the training-tape entries, inference only
+    the fused ones (e.g. the upsample-folded phase convs), and the packs are redone after every optimizer step."""
+
+    def __init__(self, builders):
+        super().__init__()
+        self._builders = builders
+
+    def __missing__(self, key):
+        with torch.no_grad():
+            value = self._builders[key]()
+        self[key] = value
+        return value
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._builders
+
+
 class _PlanModule(nn.Module):
     """Shared machinery: lazy weight packing keyed on parameter versions; eval-only in this round's
     forward (training goes through dream_b200.autograd)."""
@@ -284,38 +302,44 @@ class DreamHourglass(_PlanModule):
         return _node_for(self, key)
 
     def _build_plan(self):
-        P = {}
-        first = self._n("layer_0_1_down.0")
+        n = self._n
+        Bd = {}
+        first = n("layer_0_1_down.0")
         if self.n_image_input_channels == 3:
-            wf = ops.pack_first_weight(first.weight, 64)
-            P["first"] = _PackedConv(wf, ops.pad_bias(first.bias, 64, wf.device), [(0, 0)], relu=True, cout=64)
+            def pack_first():
+                wf = ops.pack_first_weight(first.weight, 64)
+                return _PackedConv(wf, ops.pad_bias(first.bias, 64, wf.device), [(0, 0)], relu=True, cout=64)
+            Bd["first"] = pack_first
         else:
             # later stages of DreamHourglassMultiStage see image + previous belief maps (models.py:404-407):
             # an ordinary 9-tap layer on the input packed to 64 zero-padded channels
-            P["first"] = P["layer_0_1_down.0"] = _pack3x3(first, relu=True, cin_pad=64)
+            Bd["first"] = lambda: _pack3x3(first, relu=True, cin_pad=64)
         for block, idxs, _ in VGG_TRUNK:
             for j in idxs:
                 if block == "layer_0_1_down" and j == 0:
                     continue
-                P["%s.%d" % (block, j)] = _pack3x3(self._n("%s.%d" % (block, j)), relu=True)
+                Bd["%s.%d" % (block, j)] = lambda k="%s.%d" % (block, j): _pack3x3(n(k), relu=True)
         if self.deconv_decoder:
             for name in ("deconv_0_4", "deconv_0_3", "deconv_0_2", "deconv_0_1"):
-                P[name + ".0"] = _pack_deconv(self._n(name + ".0"), 3, relu=True)
+                Bd[name + ".0"] = lambda k=name + ".0": _pack_deconv(n(k), 3, relu=True)
                 if name != "deconv_0_1":
-                    P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
+                    Bd[name + ".2"] = lambda k=name + ".2": _pack3x3(n(k), relu=True)
         else:
             for name in ("upsample_0_4", "upsample_0_3"):
-                P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)          # training tape
-                P[name + ".4/up"] = _pack_upsampled_conv(self._n(name + ".4"), relu=True)   # inference
-                P[name + ".6"] = _pack3x3(self._n(name + ".6"), relu=False)
+                Bd[name + ".4"] = lambda k=name + ".4": _pack3x3(n(k), relu=True)              # training tape
+                Bd[name + ".4/up"] = lambda k=name + ".4": _pack_upsampled_conv(n(k), relu=True)   # inference
+                Bd[name + ".6"] = lambda k=name + ".6": _pack3x3(n(k), relu=False)
             if self.full_output:
                 for name in ("upsample_0_2", "upsample_0_1"):
-                    P[name + ".2"] = _pack3x3(self._n(name + ".2"), relu=True)
-                    P[name + ".2/up"] = _pack_upsampled_conv(self._n(name + ".2"), relu=True)
-                    P[name + ".4"] = _pack3x3(self._n(name + ".4"), relu=True)
-        P["heads_0.0"] = _pack3x3(self._n("heads_0.0"), relu=True)
-        P["heads_0.2"] = _pack3x3(self._n("heads_0.2"), relu=True)            # 32 real + 32 zero channels
-        P["heads_0.4"] = _pack3x3(self._n("heads_0.4"), relu=False, cout_pad=16, cin_pad=64)
+                    Bd[name + ".2"] = lambda k=name + ".2": _pack3x3(n(k), relu=True)
+                    Bd[name + ".2/up"] = lambda k=name + ".2": _pack_upsampled_conv(n(k), relu=True)
+                    Bd[name + ".4"] = lambda k=name + ".4": _pack3x3(n(k), relu=True)
+        Bd["heads_0.0"] = lambda: _pack3x3(n("heads_0.0"), relu=True)
+        Bd["heads_0.2"] = lambda: _pack3x3(n("heads_0.2"), relu=True)            # 32 real + 32 zero channels
+        Bd["heads_0.4"] = lambda: _pack3x3(n("heads_0.4"), relu=False, cout_pad=16, cin_pad=64)
+        P = _LazyPlan(Bd)
+        if self.n_image_input_channels != 3:
+            Bd["layer_0_1_down.0"] = lambda: P["first"]
         return P
 
     def belief_maps(self, x):

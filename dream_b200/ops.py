@@ -222,10 +222,21 @@ def pack_conv_weight(w, rs_list, cin_pad=None, cout_pad=None, scale=None):
     wf = w.detach().float()
     if scale is not None:
         wf = wf * scale.view(-1, 1, 1, 1)
+    order = [r * S + s for r, s in rs_list]
+    flat = wf.reshape(Cout, Cin, R * S)
+    if order == list(range(R * S)):                      # all taps in raster order: one permuted copy
+        taps = flat.permute(2, 0, 1)
+    elif order == list(range(R * S - 1, -1, -1)):        # ... or reversed (data gradient of a 'same' conv)
+        taps = flat.flip(2).permute(2, 0, 1)
+    else:
+        taps = torch.stack([wf[:, :, r, s] for r, s in rs_list], dim=0)
+    if Cout == cout_pad and Cin == cin_pad:
+        out = torch.empty((len(rs_list), Cout, Cin), dtype=torch.float16, device=w.device)
+        out.copy_(taps)                                  # permute + fp32 -> fp16 in one kernel
+        return out
     out = torch.zeros((len(rs_list), cout_pad, cin_pad), dtype=torch.float16, device=w.device)
-    for t, (r, s) in enumerate(rs_list):
-        out[t, :Cout, :Cin] = wf[:, :, r, s].to(torch.float16)
-    return out.contiguous()
+    out[:, :Cout, :Cin] = taps
+    return out
 
 
 def pack_first_weight(w, Kpad, cout_pad=None, scale=None):
@@ -298,6 +309,15 @@ def scale_mask_bias_(dy, y=None, scale=None):
     check(lib().dreamb200_scale_mask_bias_f16(_ptr(dy), _ptr(y), _ptr(scale), _ptr(db), dy.numel() // Cc, Cc,
                                               _stream()), "dreamb200_scale_mask_bias_f16")
     return db
+
+
+def loss_scale_step(amax, cum, target=256.0):
+    """f = 2^floor(log2(target / amax)) (clamped); cum *= f IN PLACE; returns (f, 1/cum) as 1-element cuda tensors."""
+    out = torch.empty((2,), dtype=torch.float32, device=cum.device)
+    f, inv = out[0:1], out[1:2]
+    check(lib().dreamb200_loss_scale_step(_ptr(amax), _ptr(cum), _ptr(f), _ptr(inv), float(target), _stream()),
+          "dreamb200_loss_scale_step")
+    return f, inv
 
 
 def absmax(x):

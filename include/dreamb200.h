@@ -156,6 +156,9 @@ int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long l
 /* scale_mask and the bias gradient in one pass: dy = dy*(*scale)*(y>0); db[c] += sum_rows dy (caller zeroes db) */
 int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const float* scale, float* db, long long rows, int C,
                                   void* stream);
+/* one step of the fp16 backward pass' loss re-scaling, on the device (all pointers: one device float):
+ * f = 2^floor(log2(target / max(*amax, 1e-30))) clamped to [2^-20, 2^20]; *cum *= f; *f_out = f; *inv_out = 1 / *cum */
+int dreamb200_loss_scale_step(const float* amax, float* cum, float* f_out, float* inv_out, float target, void* stream);
 /* *out = max(*out, max|x|) over n fp16 values (out: device float, zeroed by the caller) */
 int dreamb200_absmax_f16(const void* x, long long n, float* out, void* stream);
 /* autograd of nn.MaxPool2d(2) (models.py:589): x [B,H,W,C] forward input, dy [B,H/2,W/2,C].  relu_gate != 0: x is a

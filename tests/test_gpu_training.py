@@ -97,7 +97,7 @@ def test_conv_epilogue_gate_and_scale(B, H, W, Ci, Co, built_lib):
     assert (got.float() - ref).abs().max().item() <= 4 * 2.0 ** -24
     assert torch.equal(got.float() == 0, ref == 0) or bool(((got.float() == 0) | (ref.abs() <= 4 * 2.0 ** -24)).all())
     assert torch.equal((got.float() != 0) & (gate <= 0), torch.zeros_like(gate, dtype=torch.bool))
-    assert abs(amax.item() - ref.abs().max().item()) <= 1e-6
+    assert abs(amax.item() - ref.abs().max().item()) <= 1e-3 * amax.item()      # taken before the fp16 rounding
     only_scale = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, out_scale=scale)
     assert (only_scale.float() - plain.float() * 4.0).abs().max().item() <= 4 * 2.0 ** -24
 
