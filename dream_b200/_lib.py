@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
         ("relu", C.c_int32),
         ("residual_f32", C.c_void_p), ("y_f32", C.c_void_p), ("y_pool", C.c_void_p),
         ("absmax", C.c_void_p),
-        ("gate", C.c_void_p), ("out_scale", C.c_void_p),
+        ("gate", C.c_void_p), ("out_scale", C.c_void_p), ("colsum", C.c_void_p),
     ]
 
 

@@ -158,6 +158,7 @@ class _HourglassTrainFn(torch.autograd.Function):
         g = ops.nchw_to_nhwc_f16((go * f).contiguous(), 64)             # [B,h,w,64], channels >= K are zero
         amax = ops.absmax(g)            # later layers get max|dY| for free from the producing data-gradient kernel
         ready = False
+        db_ready = None                 # bias gradient of the next conv layer, when its producer already summed it
         stash = {}                      # skip connections: gradient of the skip addend, with the scale it carries
         gx = None
         fuse = _FUSE_GATES
@@ -179,6 +180,7 @@ class _HourglassTrainFn(torch.autograd.Function):
             if kind == "add":
                 stash[key] = (g.clone(), cum.clone())
                 ready = False
+                db_ready = None
                 continue
             if kind == "mark":
                 if key not in stash:            # this tensor was not used as a skip by the configured decoder
@@ -188,6 +190,7 @@ class _HourglassTrainFn(torch.autograd.Function):
                 ops.add_(g, sg)
                 amax = ops.absmax(g)
                 ready = False
+                db_ready = None
                 continue
             if kind in ("conv", "head", "first", "deconv"):
                 node = models._node_for(model, key)
@@ -197,8 +200,8 @@ class _HourglassTrainFn(torch.autograd.Function):
                     cin, cout = node.weight.shape[0], node.weight.shape[1]      # ConvTranspose2d: [Cin, Cout, 3, 3]
                 else:
                     cout, cin = node.weight.shape[0], node.weight.shape[1]
-                if ready:
-                    db = ops.bias_grad(g) if node.bias is not None else None    # mask + scale already applied
+                if ready:                                   # mask + scale already applied by the producer of g
+                    db = db_ready if db_ready is not None else (ops.bias_grad(g) if node.bias is not None else None)
                 else:
                     # ReLU mask + re-scaling + bias gradient in one pass over dY
                     f, inv = ops.loss_scale_step(amax, cum)
@@ -215,6 +218,16 @@ class _HourglassTrainFn(torch.autograd.Function):
                 # what sits below this layer's input decides how its data gradient leaves the kernel
                 gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)
                 below_is_pool = fuse and i > 0 and tape[i - 1][0] == "pool"
+                gate_t = gate if below_is_conv else None
+                if below_is_pool and i > 1:
+                    # the pooled tensor is a max over ReLU outputs: gating by it here equals gating inside the pool
+                    # backward, and lets this kernel also sum the bias gradient of the conv below the pool
+                    g2, conv2 = producer_of(i - 2)
+                    if conv2 and g2 is not None:
+                        gate_t = xin
+                db_ready = None
+                if gate_t is not None or below_is_conv:
+                    db_ready = torch.zeros((xin.shape[3],), dtype=torch.float32, device=g.device)
                 g_in = g
                 cum_in = cum.clone() if DEBUG_CAPTURE is not None else None
                 f_out = None
@@ -233,27 +246,30 @@ class _HourglassTrainFn(torch.autograd.Function):
                     rs = [(r, s_) for r in range(3) for s_ in range(3)]
                     wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
                     g = ops.conv_taps(g, wd, None, ops.TAPS_3x3, H, W, stride=2, absmax=amax,
-                                      gate=gate if below_is_conv else None, out_scale=f_out)
+                                      gate=gate_t, out_scale=f_out, colsum=db_ready)
                 else:
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3)[:, :cout, :cin]               # [9, co, ci]
                     grads[key + ".weight"] = (dw * inv_here).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
                     g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax,
-                                      gate=gate if below_is_conv else None, out_scale=f_out)
+                                      gate=gate_t, out_scale=f_out, colsum=db_ready)
                 ready = below_is_conv            # (below a pool the ReLU gate is applied by the pool backward)
                 if DEBUG_CAPTURE is not None:
                     # (key, dY fed to the kernels, its scale, layer input, dX produced, ReLU gate folded into dX, dX's scale)
-                    DEBUG_CAPTURE.append((key, g_in, cum_in, xin, g.clone(),
-                                          gate if below_is_conv else None, cum.clone()))
+                    DEBUG_CAPTURE.append((key, g_in, cum_in, xin, g.clone(), gate_t, cum.clone()))
             elif kind == "pool":
                 gate, below_is_conv = producer_of(i - 1) if (fuse and i > 0) else (None, False)
                 g = ops.maxpool2_bwd(xin, g, relu_gate=below_is_conv and gate is not None)
                 # the re-scaling for the layer below was folded into the data-gradient conv above the pool (`f_out`),
-                # the pool backward adds that layer's ReLU gate; max|g| does not grow, so `amax` stays a bound
+                # the ReLU gate of that layer is applied here (and, for the bias sum, already by the conv above);
+                # max|g| does not grow, so `amax` stays a bound and a column sum taken above stays the bias gradient
                 ready = below_is_conv
+                if not ready:
+                    db_ready = None
             elif kind == "up":
                 g = ops.upsample2_bwd(g)        # sums 4 values: the stale `amax` can under-estimate by <= 4x (256x headroom)
                 ready = False
+                db_ready = None
         ctx.tape = None
         return (None, gx) + tuple(grads.get(n) for n in ctx.param_names)
 

@@ -30,6 +30,7 @@ struct ConvParams {
   float* absmax;    // optional: running max |output| (bits of a non-negative float), see dreamb200_conv_desc
   const __half* gate;      // optional ReLU gate of the backward pass: output zeroed where gate <= 0
   const float* out_scale;  // optional device scalar multiplied into every output
+  float* colsum;           // optional [Cout_pad]: += sum over output pixels (after gate / scale): a bias gradient
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
@@ -72,7 +73,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
                                                    int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
-                                                   int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0) {
+                                                   int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0,
+                                                   float* csum = nullptr) {
   constexpr int kEpiThreads = 128 * SPLIT;
   constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
@@ -162,6 +164,24 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      }
+      if (p.colsum != nullptr) {
+        // column sums over the warp's 32 rows by a halving butterfly (31 shuffles): lane i ends up with column i
+        float r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = valid ? f[i] : 0.0f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int k = 0; k < off; ++k) {
+            const float send = up ? r[k] : r[k + off];
+            const float keep = up ? r[k + off] : r[k];
+            r[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        if (p.n_tiles == 1) csum[c * 2 + h] += r[0];       // single channel tile: accumulate across the CTA's tiles
+        else atomicAdd(p.colsum + n * BLOCK_N + c * 64 + h * 32 + lane, r[0]);
       }
       if (p.absmax != nullptr) {
         float m = 0.0f;
@@ -264,6 +284,19 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       tma_store_commit();
     }
   }
+}
+
+// After a CTA's last tile: add the per-warp column sums kept in `csum` (see epilogue_nhwc_tile) to p.colsum.
+template <int BLOCK_N, int SPLIT>
+__device__ __forceinline__ void flush_colsum(const ConvParams& p, const float* csum, int lane, int hsel) {
+  if (p.colsum == nullptr || p.n_tiles != 1) return;
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N / 64; ++c)
+#pragma unroll 1
+    for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+      const int h = SPLIT == 2 ? hsel : hh;
+      atomicAdd(p.colsum + c * 64 + h * 32 + lane, csum[c * 2 + h]);
+    }
 }
 
 // Cooperative copy of the first output-channel tile's fp32 bias into shared memory (call before the prologue

@@ -211,6 +211,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t accph = 0;
     uint32_t chunk_ctr = 0;
+    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, tx, ty, b;
       decode_tile(p, tile, n, tx, ty, b);
@@ -225,11 +226,12 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
         epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                  tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid,
-                                                 chunk_ctr, hsel);
+                                                 chunk_ctr, hsel, csum);
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
     }
+    flush_colsum<BLOCK_N, kRsEpiSplit>(p, csum, lane, hsel);
     if (epi_tid == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
@@ -256,6 +258,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.absmax = d->absmax;
   p.gate = reinterpret_cast<const __half*>(d->gate);
   p.out_scale = d->out_scale;
+  p.colsum = d->colsum;
   p.mg_n = div_magic(p.n_tiles);
   p.mg_x = div_magic(p.tiles_x);
   p.mg_y = div_magic(p.tiles_y);

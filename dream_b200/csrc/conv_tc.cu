@@ -155,6 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
+    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, tx, ty, b;
       decode_tile(p, tile, n, tx, ty, b);
@@ -167,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
         epilogue_nhwc_tile<BLOCK_N, kTcSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                               tempty_bar(as), n, tx, ty, b, ox, oy, valid, row, lane, epi_tid,
-                                              chunk_ctr, hsel);
+                                              chunk_ctr, hsel, csum);
       } else {
         // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
         uint32_t v[16];
@@ -192,6 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) flush_colsum<BLOCK_N, kTcSplit>(p, csum, lane, hsel);
     if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && epi_tid == 0) tma_store_wait_read<0>();
   }
 
@@ -299,6 +301,7 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
   p.absmax = d->absmax;
   p.gate = reinterpret_cast<const __half*>(d->gate);
   p.out_scale = d->out_scale;
+  p.colsum = d->colsum;
   p.mg_n = div_magic(p.n_tiles);
   p.mg_x = div_magic(p.tiles_x);
   p.mg_y = div_magic(p.tiles_y);

@@ -33,7 +33,7 @@ def round_up(v, m):
 
 def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=None,
               y_strides=None, head_cout=None, y_offset=0, residual_f32=None, y_f32=None, pool=None, absmax=None,
-              gate=None, out_scale=None):
+              gate=None, out_scale=None, colsum=None):
     """Sum-of-shifted-GEMMs convolution on the tensor cores (dreamb200_conv2d_fwd).
 
     x: [B,H,W,Cin] fp16 contiguous; w: [T,Cout_pad,Cin] fp16; bias fp32 [Cout_pad] or None;
@@ -89,6 +89,9 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         assert gate.dtype == torch.float16 and gate.is_contiguous() and tuple(gate.shape) == (B, Ho, Wo, Cout_pad)
         assert head_cout is None and pool is None
         d.gate = gate.data_ptr()
+    if colsum is not None:          # fp32 [Cout_pad] (zeroed): += per-channel sum of the outputs over all pixels
+        assert colsum.dtype == torch.float32 and colsum.numel() == Cout_pad and head_cout is None and pool is None
+        d.colsum = colsum.data_ptr()
     if out_scale is not None:       # 1-element fp32 cuda tensor multiplied into every output
         assert out_scale.dtype == torch.float32 and out_scale.numel() == 1 and head_cout is None
         d.out_scale = out_scale.data_ptr()

@@ -68,6 +68,9 @@ typedef struct dreamb200_conv_desc {
      (power-of-two loss re-scaling chosen on the device).  Applied before `absmax`. */
   const void* gate;
   const float* out_scale;
+  /* optional fp32 [Cout_pad], zeroed by the caller: colsum[c] += sum over all output pixels of the (gated, scaled)
+     fp32 results -- the bias gradient of the layer this data gradient flows into (NHWC_F16 mode only) */
+  float* colsum;
 } dreamb200_conv_desc;
 
 /* fraction of the 128 accumulator rows a conv with this output size keeps busy, for the free tile

@@ -91,13 +91,17 @@ def test_conv_epilogue_gate_and_scale(B, H, W, Ci, Co, built_lib):
     scale = torch.tensor([4.0], device="cuda")
     plain = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W)
     amax = torch.zeros((1,), dtype=torch.float32, device="cuda")
-    got = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, gate=gate, out_scale=scale, absmax=amax)
+    colsum = torch.zeros((Co,), dtype=torch.float32, device="cuda")
+    got = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, gate=gate, out_scale=scale, absmax=amax, colsum=colsum)
     ref = (plain.float() * 4.0) * (gate > 0)
     # a power-of-two scale commutes with the fp16 rounding except for results in the subnormal range (spacing 2^-24)
     assert (got.float() - ref).abs().max().item() <= 4 * 2.0 ** -24
     assert torch.equal(got.float() == 0, ref == 0) or bool(((got.float() == 0) | (ref.abs() <= 4 * 2.0 ** -24)).all())
     assert torch.equal((got.float() != 0) & (gate <= 0), torch.zeros_like(gate, dtype=torch.bool))
     assert abs(amax.item() - ref.abs().max().item()) <= 1e-3 * amax.item()      # taken before the fp16 rounding
+    # colsum: per-channel sum of the gated, scaled fp32 results over all pixels (a bias gradient)
+    ref_sum = ref.double().sum(dim=(0, 1, 2))
+    assert (colsum.double() - ref_sum).abs().max().item() <= 2e-3 * ref.abs().double().sum(dim=(0, 1, 2)).max().item()
     only_scale = ops.conv_taps(x, w, None, ops.TAPS_3x3, H, W, out_scale=scale)
     assert (only_scale.float() - plain.float() * 4.0).abs().max().item() <= 4 * 2.0 ** -24
 
