@@ -68,6 +68,7 @@ _PROTOS = {
     "dreamb200_maxpool3_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dreamb200_scale_mask_bias_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "dreamb200_wgrad_first3x3": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p]),
     "dreamb200_loss_scale_step": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p]),
     "dreamb200_absmax_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "dreamb200_maxpool2_bwd_nhwc": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),

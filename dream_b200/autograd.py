@@ -46,7 +46,11 @@ class _HourglassTrainFn(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         P = model.plan()
         tape = []          # (kind, key, input, output)
-        if model.n_image_input_channels == 3:
+        if model.n_image_input_channels == 3 and ops.wgrad_first_supported(x):
+            # fused gather + pack + conv (first_conv.cu); its weight gradient is taken straight from x as well
+            y = ops.first_conv3x3(x, P["first"].w, P["first"].b)
+            tape.append(("first", "layer_0_1_down.0", x, y))
+        elif model.n_image_input_channels == 3:
             t = ops.im2col_first(x, 3, 3, 1, 1, 64)
             y = models._run_conv(P["first"], t)
             tape.append(("first", "layer_0_1_down.0", t, y))
@@ -209,7 +213,10 @@ class _HourglassTrainFn(torch.autograd.Function):
                 if node.bias is not None:
                     grads[key + ".bias"] = db[:cout] * inv
                 if kind == "first":
-                    dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]                   # [co, (r,s,c)]
+                    if xin.dtype == torch.float32:                                     # the raw input (fused path)
+                        dw = ops.wgrad_first(g, xin)[:cout]                            # [co, (r,s,c)]
+                    else:                                                              # the im2col'ed input
+                        dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]
                     grads[key + ".weight"] = (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
                     if DEBUG_CAPTURE is not None:
                         DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None, None, None))

@@ -314,6 +314,28 @@ def scale_mask_bias_(dy, y=None, scale=None):
     return db
 
 
+def wgrad_first_supported(x):
+    return x.shape[3] % 4 == 0 and x.data_ptr() % 16 == 0
+
+
+def wgrad_first(dy, x):
+    """Weight gradient of the first 3x3 conv straight from the fp32 NCHW input (no im2col tensor):
+    dy fp16 [B,H,W,64], x fp32 [B,3,H,W] -> fp32 [64, 27] with k = (r*3+s)*3+c."""
+    B, H, W_, Co = dy.shape
+    assert Co == 64 and dy.dtype == torch.float16 and dy.is_contiguous()
+    assert x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (B, 3, H, W_)
+    dw = torch.zeros((64, 64), dtype=torch.float32, device=dy.device)
+    e0 = e1 = None
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().dreamb200_wgrad_first3x3(_ptr(dy), _ptr(x), _ptr(dw), B, H, W_, _stream()), "dreamb200_wgrad_first3x3")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("wgrad_first3x3 %dx%d" % (H, W_), 2.0 * B * H * W_ * 64 * 27, e0, e1))
+    return dw[:, :27]
+
+
 def loss_scale_step(amax, cum, target=256.0):
     """f = 2^floor(log2(target / amax)) (clamped); cum *= f IN PLACE; returns (f, 1/cum) as 1-element cuda tensors."""
     out = torch.empty((2,), dtype=torch.float32, device=cum.device)

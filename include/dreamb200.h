@@ -159,6 +159,10 @@ int dreamb200_scale_mask_f16(void* dy, const void* y, const float* scale, long l
 /* scale_mask and the bias gradient in one pass: dy = dy*(*scale)*(y>0); db[c] += sum_rows dy (caller zeroes db) */
 int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const float* scale, float* db, long long rows, int C,
                                   void* stream);
+/* weight gradient of the first 3x3 convolution (models.py:591-599) without a patch tensor: dy fp16 NHWC [B,H,W,64],
+ * x fp32 NCHW [B,3,H,W] (W % 4 == 0), dw fp32 [64][64] zeroed by the caller:
+ * dw[co][(r*3+s)*3+c] += sum_p dy[p][co] * x[p + (r-1, s-1)][c] */
+int dreamb200_wgrad_first3x3(const void* dy, const float* x, float* dw, int B, int H, int W, void* stream);
 /* one step of the fp16 backward pass' loss re-scaling, on the device (all pointers: one device float):
  * f = 2^floor(log2(target / max(*amax, 1e-30))) clamped to [2^-20, 2^20]; *cum *= f; *f_out = f; *inv_out = 1 / *cum */
 int dreamb200_loss_scale_step(const float* amax, float* cum, float* f_out, float* inv_out, float target, void* stream);

@@ -45,6 +45,26 @@ def test_wgrad_kernel_matches_torch(built_lib):
         assert _rel(dw, ref) <= 2e-3, (B, H, W, Ci, Co, _rel(dw, ref))
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 80), (1, 37, 52), (3, 400, 400)])
+def test_first_layer_wgrad_without_patch_tensor(B, H, W, built_lib):
+    """dreamb200_wgrad_first3x3 (input patches built in shared memory) vs the im2col + 1-tap wgrad path (same fp16
+    operands) and vs torch autograd of the layer in fp32 on the fp16-rounded operands."""
+    import torch.nn.functional as F
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.rand((B, 3, H, W), device="cuda", generator=g) * 2 - 1
+    dy = (torch.randn((B, H, W, 64), device="cuda", generator=g) * 0.5).half()
+    assert ops.wgrad_first_supported(x)
+    dw = ops.wgrad_first(dy, x)                                              # [64, 27], k = (r*3+s)*3+c
+    dw2 = ops.wgrad(dy, ops.im2col_first(x, 3, 3, 1, 1, 64), [(0, 0)])[0, :64, :27]
+    xr = x.half().float()
+    w = torch.zeros((64, 3, 3, 3), device="cuda", requires_grad=True)
+    F.conv2d(xr, w, None, padding=1).backward(dy.permute(0, 3, 1, 2).float())
+    ref = w.grad.permute(0, 2, 3, 1).reshape(64, 27)
+    assert _rel(dw, ref) <= 2e-3, _rel(dw, ref)
+    assert _rel(dw, dw2) <= 1e-3, _rel(dw, dw2)
+
+
 def test_streaming_backward_kernels_match_torch(built_lib):
     import torch.nn.functional as F
     from dream_b200 import ops
