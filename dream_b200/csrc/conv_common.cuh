@@ -74,7 +74,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
                                                    int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
                                                    int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0,
-                                                   float* csum = nullptr) {
+                                                   float* csum = nullptr, const float* breg = nullptr) {
   constexpr int kEpiThreads = 128 * SPLIT;
   constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
@@ -107,16 +107,27 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
       tmem_wait_ld();
       float f[32];
-      const uint32_t bias_addr = smem_bias + (uint32_t)(c * 64 + h * 32) * 4u;
+      if (p.bias == nullptr) {
+        // (data-gradient launches have no bias: skip the shared-memory reads -- a broadcast LDS.128 still costs
+        //  four wavefronts, and the 64-channel layers are bound by shared-memory bandwidth)
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float b0, b1, b2, b3;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_addr + (uint32_t)i * 4u));
-        f[i] = __uint_as_float(v[i]) + b0;
-        f[i + 1] = __uint_as_float(v[i + 1]) + b1;
-        f[i + 2] = __uint_as_float(v[i + 2]) + b2;
-        f[i + 3] = __uint_as_float(v[i + 3]) + b3;
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      } else if (BLOCK_N == 64 && SPLIT == 2 && breg != nullptr) {
+        // single channel tile, 32 columns per thread: the bias lives in registers for the CTA's lifetime
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + breg[i];
+      } else {
+        const uint32_t bias_addr = smem_bias + (uint32_t)(c * 64 + h * 32) * 4u;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float b0, b1, b2, b3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_addr + (uint32_t)i * 4u));
+          f[i] = __uint_as_float(v[i]) + b0;
+          f[i + 1] = __uint_as_float(v[i + 1]) + b1;
+          f[i + 2] = __uint_as_float(v[i + 2]) + b2;
+          f[i + 3] = __uint_as_float(v[i + 3]) + b3;
+        }
       }
       if (res_row != nullptr) {
 #pragma unroll

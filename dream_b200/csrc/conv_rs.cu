@@ -212,6 +212,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t accph = 0;
     uint32_t chunk_ctr = 0;
     float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float breg[32];
+    const bool bias_regs = BLOCK_N == 64 && p.n_tiles == 1 && p.bias != nullptr;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) breg[i] = bias_regs ? __ldg(p.bias + hsel * 32 + i) : 0.0f;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, tx, ty, b;
       decode_tile(p, tile, n, tx, ty, b);
@@ -226,7 +230,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
         epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                  tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid,
-                                                 chunk_ctr, hsel, csum);
+                                                 chunk_ctr, hsel, csum, bias_regs ? breg : nullptr);
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
