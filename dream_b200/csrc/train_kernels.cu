@@ -393,6 +393,182 @@ static int wgrad3x3_impl(const void* dy, const void* x, float* dw, int B, int H,
 }
 
 // ---------------------------------------------------------------------------------------------
+// wgrad for 3x3 / stride 1 / pad 1 with at most 64 output channels: ALL nine taps in one CTA, operands read ONCE.
+// The dY operand needs only 64 of the MMA's 128 M rows, so the other 64 rows carry a second VIEW of the same
+// shared-memory slab -- dY one image row further down (leading-dimension offset = one tile row = 1024 B): accumulator
+// rows 0..63 then see tap row (rho), rows 64..127 tap row (rho - 1) of whatever X view the B operand presents.  B
+// presents three column shifts at once (N = 3 x 64, chunk stride 128 B = one pixel of the halo slab) and the image
+// row shift rho through its start address.  Two MMAs per 16 pixels (rho = 0, 1) produce taps
+//   rho = 0: rows 0..63 -> dy =  0, rows 64..127 -> dy = -1;   rho = 1: rows 0..63 -> dy = +1 (rows 64..127: dy = 0
+// again, discarded): 9 of 12 computed products are used, every byte of dY and X is fetched once instead of three
+// times (the row kernel above splits the kernel rows across CTAs) and no MMA row multiplies TMA zero fill.
+// The tile grid starts at image row -1 so that the shifted view covers row 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int kC64ABytes = 18 * 1024;        // 17 image rows x 8 pixels x 128 B (17408), padded to the swizzle period
+constexpr int kC64BBytes = 22 * 1024;        // 17 image rows x 10 pixels x 128 B (21760), padded
+constexpr int kC64StageBytes = kC64ABytes + kC64BBytes;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                    const __grid_constant__ Wgrad3Params p) {
+  constexpr uint32_t kIdesc = umma_idesc_f16_m128_mn(192);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * kC64StageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * stages);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 1);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int ci_t = blockIdx.x % p.ci_tiles;
+  const int split = blockIdx.x / p.ci_tiles;
+  const long long kb_lo = p.kblocks_total * split / p.splits;
+  const long long kb_hi = p.kblocks_total * (split + 1) / p.splits;
+  const int n_kb = (int)(kb_hi - kb_lo);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int tiles = p.tiles_x * p.tiles_y;
+      for (long long kb = kb_lo; kb < kb_hi; ++kb) {
+        const int b = (int)(kb / tiles);
+        const int rr = (int)(kb - (long long)b * tiles);
+        const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+        const int x0 = tx * 8, y0 = ty * 16 - 1;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * kC64StageBytes;
+        mbar_expect_tx(full_bar(stage), (uint32_t)(17 * 8 * 128 + 17 * 10 * 128));
+        tma_load_4d(sa, &tmDY, full_bar(stage), 0, x0, y0, b);
+        tma_load_4d(sa + kC64ABytes, &tmX, full_bar(stage), ci_t * 64, x0 - 1, y0, b);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kC64StageBytes;
+        const uint32_t sb = sa + kC64ABytes;
+#pragma unroll
+        for (int rho = 0; rho < 2; ++rho) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
+            const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, 1024u);
+            const uint64_t bdesc = umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j + rho) * 1280u, 128u, 1280u);
+            umma_f16(tmem_base + (uint32_t)(rho * 192), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else if (n_kb > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int co = row & 63, half = row >> 6;          // half 1 = the view shifted one image row down
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int rho = 0; rho < 2; ++rho) {
+      if (rho == 1 && half == 1) continue;             // (dy = 0 a second time)
+      const int tap_dy = rho - half;                   // -1, 0, +1
+#pragma unroll 1
+      for (int sg = 0; sg < 3; ++sg) {
+        float* out = p.dw + ((size_t)((tap_dy + 1) * 3 + sg) * p.Cout_pad + co) * p.Cin_pad + ci_t * 64;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rho * 192 + sg * 64 + c * 32), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(out + c * 32 + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int wgrad3x3_c64_impl(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin_pad,
+                             cudaStream_t stream) {
+  Wgrad3Params p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = (W + 7) / 8;
+  p.tiles_y = (H + 1 + 15) / 16;                   // tile rows start at image row -1
+  p.co_tiles = 1;
+  p.ci_tiles = Cin_pad / 64;
+  p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
+  int splits = device_sm_count() / p.ci_tiles;     // one wave, see wgrad3x3_impl
+  if (splits < 1) splits = 1;
+  if ((long long)splits > p.kblocks_total) splits = (int)p.kblocks_total;
+  p.splits = splits;
+  p.dw = dw;
+  p.Cout_pad = 64;
+  p.Cin_pad = Cin_pad;
+  CUtensorMap tmDY, tmX;
+  const uint32_t es[4] = {1, 1, 1, 1};
+  {
+    const uint32_t box[4] = {64, 8, 17, 1};
+    uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+    if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad3 c64 dY")) return -1;
+  }
+  {
+    const uint32_t box[4] = {64, 10, 17, 1};
+    uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
+    if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad3 c64 X")) return -1;
+  }
+  int stages = (232448 - 1024 - 512) / kC64StageBytes;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * kC64StageBytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int grid = p.splits * p.ci_tiles;
+  wgrad3x3_c64_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // streaming kernels
 // ---------------------------------------------------------------------------------------------
 // dy = dy * scale * (y > 0): ReLU backward fused with the dynamic loss re-scaling; y and scale optional
@@ -823,6 +999,13 @@ extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, 
   bool std3x3 = use_row_kernel && taps == 9 && dy && x && dw && tap_dy && tap_dx && Cout_pad % 64 == 0 &&
                 Cin_pad % 64 == 0 && B > 0 && H > 0 && W > 0;
   for (int t = 0; std3x3 && t < 9; ++t) std3x3 = tap_dy[t] == t / 3 - 1 && tap_dx[t] == t % 3 - 1;
+  static int use_c64 = -1;
+  if (use_c64 < 0) {
+    const char* e = getenv("DREAMB200_WGRAD_C64");    // 0 disables the all-taps kernel for <= 64 output channels
+    use_c64 = e ? atoi(e) : 1;
+  }
+  if (std3x3 && use_c64 && Cout_pad == 64)
+    return wgrad3x3_c64_impl(dy, x, dw, B, H, W, Cin_pad, (cudaStream_t)stream_v);
   if (std3x3) return wgrad3x3_impl(dy, x, dw, B, H, W, Cout_pad, Cin_pad, (cudaStream_t)stream_v);
   return wgrad_impl(dy, x, dw, B, H, W, H, W, H, W, 1, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
                     (cudaStream_t)stream_v);

@@ -37,7 +37,8 @@ def _wgrad_reference(dy, x, taps):
 def test_wgrad_kernel_matches_torch(built_lib):
     from dream_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(3)
-    for (B, H, W, Ci, Co) in [(2, 16, 24, 64, 64), (3, 25, 25, 128, 256), (2, 50, 37, 256, 128)]:
+    for (B, H, W, Ci, Co) in [(2, 16, 24, 64, 64), (3, 25, 25, 128, 256), (2, 50, 37, 256, 128), (1, 37, 53, 128, 64),
+                              (2, 1, 9, 64, 64), (3, 100, 100, 64, 64), (2, 31, 16, 192, 64)]:
         x = (torch.randn((B, H, W, Ci), device="cuda", generator=g) * 0.5).half()
         dy = (torch.randn((B, H, W, Co), device="cuda", generator=g) * 0.5).half()
         dw = ops.wgrad(dy, x, ops.TAPS_3x3)                         # [9, Co, Ci]
