@@ -373,8 +373,14 @@ int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   // tile (streamed-weight layers); DREAMB200_RS_HALO: one 10-pixel slab serves all horizontal taps.
   static const int pair = env_flag("DREAMB200_RS_PAIR", 1);
   static const int halo = env_flag("DREAMB200_RS_HALO", 1);
+  // DREAMB200_RS_RESIDENT_WIDE: keep all 9 x Cin/64 weight tiles resident also for 64 -> 128 and 128 -> 64 channels
+  // (144 KB of weights + two activation slabs): no weight re-streaming per tile, 16-row tiles (no pair padding).
+  static const int res_wide = env_flag("DREAMB200_RS_RESIDENT_WIDE", 1);
   int rc;
-  if (d->Cout_pad % 128 == 0) {
+  if (res_wide && halo && d->y_pool == nullptr &&
+      ((d->Cout_pad == 128 && d->Cin == 64) || (d->Cout_pad == 64 && d->Cin == 128))) {
+    rc = d->Cout_pad == 128 ? launch_rs<128, true, 1, true>(d, stream) : launch_rs<64, true, 1, true>(d, stream);
+  } else if (d->Cout_pad % 128 == 0) {
     if (pair && halo) rc = launch_rs<128, false, 2, true>(d, stream);
     else if (pair) rc = launch_rs<128, false, 2, false>(d, stream);
     else if (halo) rc = launch_rs<128, false, 1, true>(d, stream);
