@@ -48,7 +48,9 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, ui
 constexpr int kRsEpiSplit = 2;                          // 8 epilogue warps (see conv_common.cuh)
 constexpr int kRsThreads = 64 + 128 * kRsEpiSplit;
 
-template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO>
+// HEAD    : the network head -- BLOCK_N = 16 accumulator columns of which the first cout_real are channels, written as
+//           fp32 NCHW straight from the accumulators (no staging, no TMA store); resident weights only.
+template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO, bool HEAD = false>
 __global__ void __launch_bounds__(kRsThreads, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
@@ -72,7 +74,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_a = smem_base;                                    // sa slabs
   const uint32_t smem_b = smem_a + sa * kSlabBytes;                     // sb tiles (ring) or n_wtiles tiles (resident)
   const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : sb) * kBBytes;
-  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
+  const uint32_t smem_pool = smem_out + (HEAD ? 0 : 2 * kStageOutBytes);
   const uint32_t bar_base = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
   auto afull = [&](int s) { return bar_base + 8u * s; };
   auto aempty = [&](int s) { return bar_base + 8u * (sa + s); };
@@ -92,7 +94,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
+    if (!HEAD) tma_prefetch_desc(&tmC);
     if (p.pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < sa; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
     for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
@@ -221,6 +223,32 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode_tile(p, tile, n, tx, ty, b);
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
+      if constexpr (HEAD) {
+        // fp32 NCHW head: this warp's 8 of the 16 accumulator columns (hsel), channels < cout_real are real
+        const int ox = tx * kRsTw + lx, oy = ty * kRsTh + ly;
+        uint32_t v[8];
+        tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + hsel * 8), v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (ox < p.Wo && oy < p.Ho) {
+          const size_t plane = (size_t)p.Ho * p.Wo;
+          float* o = p.out_f32 + (size_t)b * p.cout_real * plane + (size_t)oy * p.Wo + ox;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ch = hsel * 8 + k;
+            if (ch < p.cout_real) {
+              float f = __uint_as_float(v[k]) + smem_bias_gen[ch];
+              if (p.relu) f = fmaxf(f, 0.0f);
+              o[(size_t)ch * plane] = f;
+            }
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) accph ^= 1u;
+        continue;
+      }
 #pragma unroll 1
       for (int sub = 0; sub < SUBTILES; ++sub) {
         const int tys = ty * SUBTILES + sub;                  // 16-row tile index of this sub-tile
@@ -235,8 +263,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
     }
-    flush_colsum<BLOCK_N, kRsEpiSplit>(p, csum, lane, hsel);
-    if (epi_tid == 0) tma_store_wait_read<0>();
+    if constexpr (!HEAD) {
+      flush_colsum<BLOCK_N, kRsEpiSplit>(p, csum, lane, hsel);
+      if (epi_tid == 0) tma_store_wait_read<0>();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -246,7 +276,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO>
+template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO, bool HEAD = false>
 static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -275,14 +305,16 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.y_f32 = d->y_f32;
   p.Cout_pad = d->Cout_pad;
   p.relu = d->relu;
-  p.pool = d->y_pool != nullptr ? 1 : 0;
+  p.pool = (!HEAD && d->y_pool != nullptr) ? 1 : 0;
   p.store_full = d->y != nullptr ? 1 : 0;
+  p.out_f32 = HEAD ? reinterpret_cast<float*>(d->y) : nullptr;
+  p.cout_real = d->cout_real;
 
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kRows = kRsTh * SUBTILES + 2;
   constexpr int kPitch = HALO ? 1280 : 1024;
   constexpr int kSlabBytes = ((kRows * kPitch + 1023) / 1024) * 1024;
-  const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
+  const int out_bytes = HEAD ? 0 : 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
   RsExtra x;
   int budget = 232448 - 1024 - out_bytes - 1024 - BLOCK_N * 4;
   if (RESIDENT) {
@@ -319,7 +351,7 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t es[3] = {1, 1, 1};
     if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "rs weights")) return -1;
   }
-  if (d->y_pool != nullptr) {
+  if (!HEAD && d->y_pool != nullptr) {
     const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
     uint64_t dims[4] = {C, Wp, Hp, (uint64_t)d->B};
     uint64_t str[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
@@ -327,14 +359,14 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es, "rs pooled output")) return -1;
   }
-  if (d->y != nullptr) {
+  if (!HEAD && d->y != nullptr) {
     uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
     uint32_t box[4] = {64, kRsTw, kRsTh, 1};
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "rs output")) return -1;
   }
-  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO>;
+  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO, HEAD>;
   static bool attr_set = false;
   if (!attr_set) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -361,13 +393,21 @@ int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     const char* e = getenv("DREAMB200_RS_MIN_UTIL");   // 2.0 disables the kernel (A/B measurements)
     min_util = e ? atof(e) : 0.85;
   }
-  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->taps != 9 || d->in_stride != 1) return 0;
+  if (d->taps != 9 || d->in_stride != 1) return 0;
   if (d->Ho != d->H || d->Wo != d->W) return 0;
   if (d->Cout_pad % 256 == 0) return 0;                 // wide layers are tensor-bound already in conv_tc
   for (int t = 0; t < 9; ++t)
     if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1) return 0;
   const double util = (double)d->Wo * d->Ho /
                       ((double)((d->Wo + kRsTw - 1) / kRsTw) * ((d->Ho + kRsTh - 1) / kRsTh) * 128.0);
+  if (d->out_mode == DREAMB200_OUT_NCHW_F32) {
+    // the fp32 NCHW head (Cout_pad == 16): one slab per tile instead of nine 16 KB tap tiles from L2
+    static const int head = env_flag("DREAMB200_RS_HEAD", 1);
+    if (!head || d->Cout_pad != 16 || d->Cin != 64 || util < 0.5) return 0;
+    const int rc = launch_rs<16, true, 1, true, true>(d, stream);
+    return rc == 0 ? 1 : rc;
+  }
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16) return 0;
   if (util < min_util) return 0;
   // variants (env overrides are for A/B measurements): DREAMB200_RS_PAIR: two stacked tiles share each weight
   // tile (streamed-weight layers); DREAMB200_RS_HALO: one 10-pixel slab serves all horizontal taps.

@@ -417,6 +417,10 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
     DB_REQUIRE(d->cout_real >= 1 && d->cout_real <= 16, "conv: cout_real=%d out of range", d->cout_real);
     DB_REQUIRE(d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr,
                "conv: residual / fp32 stream unsupported for the NCHW_F32 head");
+    {
+      const int r = try_conv_rs(d, stream);    // slab kernel when the head is a plain 3x3 over 64 (padded) channels
+      if (r != 0) return r > 0 ? 0 : r;
+    }
     return launch<16, DREAMB200_OUT_NCHW_F32>(d, stream, sms);
   }
   DB_REQUIRE(d->out_mode == DREAMB200_OUT_NHWC_F16, "conv: unknown out_mode %d", d->out_mode);

@@ -107,6 +107,9 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         block_n = 16 if head_cout is not None else (256 if Cout_pad % 256 == 0 else 128 if Cout_pad % 128 == 0 else 64)
         rs = (T == 9 and stride == 1 and block_n in (64, 128) and tuple(taps) == tuple(TAPS_3x3) and
               Ho * Wo / (((Wo + 7) // 8) * ((Ho + 15) // 16) * 128.0) >= float(os.environ.get("DREAMB200_RS_MIN_UTIL", 0.85)))
+        if head_cout is not None:      # the head takes the slab kernel whenever it is a plain 3x3 over 64 padded channels
+            rs = (T == 9 and stride == 1 and Cin == 64 and tuple(taps) == tuple(TAPS_3x3) and
+                  os.environ.get("DREAMB200_RS_HEAD", "1") != "0")
         tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % ("conv_rs" if rs else "conv_tc", block_n, T, Cin, Cout_pad, Ho, Wo, stride)
         PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
     else:
