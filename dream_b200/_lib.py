@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdreamb200.so")
+# DREAMB200_LIB: another build of the same library (A/B measurements of kernel variants, tools/layer_bench.py)
+LIB_PATH = os.environ.get("DREAMB200_LIB") or os.path.join(_HERE, "libdreamb200.so")
 MAX_TAPS = 16
 OUT_NHWC_F16 = 0
 OUT_NCHW_F32 = 1

@@ -76,9 +76,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must become a trapped launch, never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must become a trapped launch, never a hung GPU.  The polling loop is out of line:
+// inlined at every wait it bloated the (instruction-cache resident) issue loops.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -88,6 +88,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---- proxies / fences ----
@@ -163,6 +168,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// ---- warp-converged issue ----
+// tcgen05.mma / tcgen05.commit are single-thread instructions.  Issued under `if (lane == 0)` the compiler cannot
+// prove that one thread is active and wraps EVERY instruction in an elect / branch loop (~60 cycles per MMA,
+// measured: the issuing warp of the 64-channel kernels spent 73 % of its time there, not waiting for operands).
+// Issued from warp-uniform control flow under elect.sync the same code becomes back-to-back UTCHMMA.  elect.sync
+// elects the same lane for the same member mask every time, so commits track the MMAs issued before them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred px;\n"
+      "elect.sync _|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

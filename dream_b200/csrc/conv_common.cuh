@@ -215,8 +215,12 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar_addr);
     }
-    if (epi_tid == 0) {                                // stores that used obuf / pbuf two chunks ago have read them
-      if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+    // (bulk-store bookkeeping by ONE lane of the first epilogue warp: elect.sync picks the same lane every time, and
+    //  issued from warp-uniform control flow the TMA instructions need no per-instruction election loop)
+    if (epi_tid < 32) {                                // stores that used obuf / pbuf two chunks ago have read them
+      if (elect_one()) {
+        if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+      }
     }
     named_bar_sync(1, kEpiThreads);
     const uint32_t j0 = SPLIT == 2 ? (uint32_t)hsel * 4u : 0u;      // first 16-byte chunk this thread owns
@@ -256,9 +260,11 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     }
     fence_proxy_async_smem();
     named_bar_sync(1, kEpiThreads);
-    if (epi_tid == 0 && (!p.pool || p.store_full)) {
-      tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
-      tma_store_commit();
+    if (epi_tid < 32 && (!p.pool || p.store_full)) {
+      if (elect_one()) {
+        tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
+        tma_store_commit();
+      }
     }
     if (p.pool && !shfl_pool) {
       // generic tile shape: 2x2 max over the tile that now sits in obuf (pooled row pr, 16 B chunk ch per item)
@@ -290,9 +296,11 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       fence_proxy_async_smem();
       named_bar_sync(1, kEpiThreads);
     }
-    if (p.pool && epi_tid == 0) {
-      tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * (p.tw >> 1), ty * (p.th >> 1), b);
-      tma_store_commit();
+    if (p.pool && epi_tid < 32) {
+      if (elect_one()) {
+        tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * (p.tw >> 1), ty * (p.th >> 1), b);
+        tma_store_commit();
+      }
     }
   }
 }

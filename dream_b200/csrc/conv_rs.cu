@@ -109,13 +109,16 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) ==========
+    {
       if (RESIDENT) {   // this CTA's n is fixed (n_tiles == 1 for resident layers): all weight tiles once
-        mbar_expect_tx(wbar, (uint32_t)(n_wtiles * kBBytes));
-        for (int tap = 0; tap < 9; ++tap)
-          for (int kc = 0; kc < p.kchunks; ++kc)
-            tma_load_3d(smem_b + (tap * p.kchunks + kc) * kBBytes, &tmB, wbar, kc * 64, 0, tap);
+        if (elect_one()) {
+          mbar_expect_tx(wbar, (uint32_t)(n_wtiles * kBBytes));
+          for (int tap = 0; tap < 9; ++tap)
+            for (int kc = 0; kc < p.kchunks; ++kc)
+              tma_load_3d(smem_b + (tap * p.kchunks + kc) * kBBytes, &tmB, wbar, kc * 64, 0, tap);
+        }
+        __syncwarp();
       }
       int as_ = 0, bs_ = 0;
       uint32_t aph = 0, bph = 0;
@@ -127,15 +130,19 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int s = 0; s < 3; ++s) {
             if (!HALO || s == 0) {
               mbar_wait(aempty(as_), aph ^ 1u);
-              mbar_expect_tx(afull(as_), (uint32_t)kSlabTx);
-              tma_load_4d(smem_a + as_ * kSlabBytes, &tmA, afull(as_), kc * 64, x0 - 1 + (HALO ? 0 : s), y0 - 1, b);
+              if (elect_one()) {
+                mbar_expect_tx(afull(as_), (uint32_t)kSlabTx);
+                tma_load_4d(smem_a + as_ * kSlabBytes, &tmA, afull(as_), kc * 64, x0 - 1 + (HALO ? 0 : s), y0 - 1, b);
+              }
               if (++as_ == sa) { as_ = 0; aph ^= 1u; }
             }
             if (!RESIDENT) {
               for (int r = 0; r < 3; ++r) {
                 mbar_wait(bempty(bs_), bph ^ 1u);
-                mbar_expect_tx(bfull(bs_), (uint32_t)kBBytes);
-                tma_load_3d(smem_b + bs_ * kBBytes, &tmB, bfull(bs_), kc * 64, n * BLOCK_N, r * 3 + s);
+                if (elect_one()) {
+                  mbar_expect_tx(bfull(bs_), (uint32_t)kBBytes);
+                  tma_load_3d(smem_b + bs_ * kBBytes, &tmB, bfull(bs_), kc * 64, n * BLOCK_N, r * 3 + s);
+                }
                 if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
               }
             }
@@ -145,8 +152,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) ==========
+    {
       if (RESIDENT) mbar_wait(wbar, 0);
       int as_ = 0, bs_ = 0;
       uint32_t aph = 0, bph = 0;
@@ -156,48 +163,67 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SUBTILES * BLOCK_N);
-        uint32_t first = 1u;
         for (int kc = 0; kc < p.kchunks; ++kc) {
+          const bool last_kc = kc == p.kchunks - 1;
           uint32_t slab = 0;
+#pragma unroll(RESIDENT ? 3 : 1)
           for (int s = 0; s < 3; ++s) {
             if (!HALO || s == 0) {
               mbar_wait(afull(as_), aph);
               tc_fence_after();
               slab = smem_a + as_ * kSlabBytes;
             }
-            for (int r = 0; r < 3; ++r) {
-              uint32_t btile;
-              if (RESIDENT) {
-                btile = smem_b + ((r * 3 + s) * p.kchunks + kc) * kBBytes;
-              } else {
+            const bool slab_done = !HALO || s == 2;
+            // vertical tap r = image-row offset into the slab; horizontal tap s (HALO only) = one pixel = 128 B.
+            // ONE election per barrier wait: the body is straight-line UTCHMMA + commits.
+            if (RESIDENT) {
+              if (elect_one()) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                  const uint64_t bdesc = umma_desc_k_sw128(smem_b + ((r * 3 + s) * p.kchunks + kc) * kBBytes);
+#pragma unroll
+                  for (int sub = 0; sub < SUBTILES; ++sub) {
+                    const uint32_t a_addr =
+                        slab + (uint32_t)((r + sub * kRsTh) * kPitch) + (HALO ? (uint32_t)s * 128u : 0u);
+                    const uint64_t adesc = umma_desc_k_sw128_sbo(a_addr, kPitch);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16(d_tmem + (uint32_t)(sub * BLOCK_N), adesc + 2u * k, bdesc + 2u * k, kIdesc,
+                               (kc | s | r | k) != 0 ? 1u : 0u);
+                  }
+                }
+                if (slab_done) umma_commit(aempty(as_));
+                if (last_kc && s == 2) umma_commit(tfull_bar(acc));
+              }
+            } else {
+#pragma unroll 1
+              for (int r = 0; r < 3; ++r) {
                 mbar_wait(bfull(bs_), bph);
                 tc_fence_after();
-                btile = smem_b + bs_ * kBBytes;
-              }
-              const uint64_t bdesc = umma_desc_k_sw128(btile);
+                if (elect_one()) {
+                  const uint64_t bdesc = umma_desc_k_sw128(smem_b + bs_ * kBBytes);
 #pragma unroll
-              for (int sub = 0; sub < SUBTILES; ++sub) {
-                // vertical tap = image-row offset; horizontal tap (HALO only) = one pixel = 128 B
-                const uint32_t a_addr = slab + (uint32_t)((r + sub * kRsTh) * kPitch) + (HALO ? (uint32_t)s * 128u : 0u);
-                const uint64_t adesc = umma_desc_k_sw128_sbo(a_addr, kPitch);
+                  for (int sub = 0; sub < SUBTILES; ++sub) {
+                    const uint32_t a_addr =
+                        slab + (uint32_t)((r + sub * kRsTh) * kPitch) + (HALO ? (uint32_t)s * 128u : 0u);
+                    const uint64_t adesc = umma_desc_k_sw128_sbo(a_addr, kPitch);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(d_tmem + (uint32_t)(sub * BLOCK_N), adesc + 2u * k, bdesc + 2u * k, kIdesc,
-                           (first && k == 0) ? 0u : 1u);
-              }
-              first = 0u;
-              if (!RESIDENT) {
-                umma_commit(bempty(bs_));
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16(d_tmem + (uint32_t)(sub * BLOCK_N), adesc + 2u * k, bdesc + 2u * k, kIdesc,
+                               (kc | s | r | k) != 0 ? 1u : 0u);
+                  }
+                  umma_commit(bempty(bs_));
+                  if (r == 2 && slab_done) umma_commit(aempty(as_));
+                  if (r == 2 && s == 2 && last_kc) umma_commit(tfull_bar(acc));
+                }
                 if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
               }
             }
-            if (!HALO || s == 2) {
-              umma_commit(aempty(as_));
+            if (slab_done) {
               if (++as_ == sa) { as_ = 0; aph ^= 1u; }
             }
           }
         }
-        umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) accph ^= 1u;
       }
@@ -265,7 +291,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if constexpr (!HEAD) {
       flush_colsum<BLOCK_N, kRsEpiSplit>(p, csum, lane, hsel);
-      if (epi_tid == 0) tma_store_wait_read<0>();
+      if (epi_tid < 32) {
+        if (elect_one()) tma_store_wait_read<0>();
+      }
     }
   }
   tc_fence_before();

@@ -92,8 +92,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = p.taps * p.kchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) ==========
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -105,9 +105,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_ab + stage * kStageBytes;
-            mbar_expect_tx(full_bar(stage), (uint32_t)(p.tw * p.th * 128 + kBBytes));
-            tma_load_4d(sa, &tmA, full_bar(stage), kc * 64, xi, yi, b);
-            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), kc * 64, n * BLOCK_N, tap);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), (uint32_t)(p.tw * p.th * 128 + kBBytes));
+              tma_load_4d(sa, &tmA, full_bar(stage), kc * 64, xi, yi, b);
+              tma_load_3d(sa + kABytes, &tmB, full_bar(stage), kc * 64, n * BLOCK_N, tap);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -115,8 +117,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow, one elected lane issues) ==========
+    {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -131,15 +133,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_ab + stage * kStageBytes;
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          if (elect_one()) {      // ONE election per k-block: the body is straight-line UTCHMMA + commits
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
-            umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+              umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(as));
           }
-          umma_commit(empty_bar(stage));
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -194,7 +198,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (as == 0) aphase ^= 1u;
     }
     if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) flush_colsum<BLOCK_N, kTcSplit>(p, csum, lane, hsel);
-    if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && epi_tid == 0) tma_store_wait_read<0>();
+    if (OUT_MODE == DREAMB200_OUT_NHWC_F16 && epi_tid < 32) {
+      if (elect_one()) tma_store_wait_read<0>();
+    }
   }
 
   tc_fence_before();

@@ -210,6 +210,9 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + 8u), "h"(__half_as_ushort(lo)) : "memory");
       }
       fence_proxy_async_smem();
+    }
+    __syncwarp();
+    {   // whole warp in uniform control flow, one elected lane issues (see elect_one in common.cuh)
       uint32_t ph[2] = {0u, 0u};
       int as = 0;
       uint32_t aphase = 0;
@@ -222,10 +225,12 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tc_fence_after();
         const uint64_t adesc = umma_desc_k_sw128(smem_a + s * kABytes);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 64);
-        umma_f16(d_tmem, adesc, bdesc, kIdesc, 0u);
-        umma_f16(d_tmem, adesc + 2u, bdesc + 2u, kIdesc, 1u);
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(as));
+        if (elect_one()) {
+          umma_f16(d_tmem, adesc, bdesc, kIdesc, 0u);
+          umma_f16(d_tmem, adesc + 2u, bdesc + 2u, kIdesc, 1u);
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(as));
+        }
         ph[s] ^= 1u;
         as ^= 1;
         if (as == 0) aphase ^= 1u;
@@ -234,7 +239,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     __syncwarp();
   } else if (warp == 9) {
     // ===================== input TMA: patches of the next kFcInStages tiles =====================
-    if (STAGED && lane == 0) {
+    if (STAGED) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         int r = tile;
@@ -243,9 +248,11 @@ first_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int b = r / p.tiles_y;
         const int is = it % kFcInStages;
         mbar_wait(in_empty(is), (uint32_t)(((it / kFcInStages) & 1) ^ 1));
-        mbar_expect_tx(in_full(is), U8 ? kFcInBytesU8 : kFcInBytesF32);
-        if (U8) tma_load_3d(smem_in + is * kFcInStride, &tmX, in_full(is), tx * kFcTw * 3 - 16, ty * kFcTh - 1, b);
-        else tma_load_4d(smem_in + is * kFcInStride, &tmX, in_full(is), tx * kFcTw - 4, ty * kFcTh - 1, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(in_full(is), U8 ? kFcInBytesU8 : kFcInBytesF32);
+          if (U8) tma_load_3d(smem_in + is * kFcInStride, &tmX, in_full(is), tx * kFcTw * 3 - 16, ty * kFcTh - 1, b);
+          else tma_load_4d(smem_in + is * kFcInStride, &tmX, in_full(is), tx * kFcTw - 4, ty * kFcTh - 1, 0, b);
+        }
       }
     }
     __syncwarp();

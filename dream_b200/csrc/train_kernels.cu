@@ -102,7 +102,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   const int n_kb = (int)(kb_hi - kb_lo);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       int stage = 0;
       uint32_t phase = 0;
       const int tiles = p.tiles_x * p.tiles_y;
@@ -113,21 +113,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int x0 = tx * kWgTw, y0 = ty * kWgTh;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * kStageBytes;
-        mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
-        const int ax = x0 * p.a_stride + (p.shift_a ? p.dx[tap] : 0), ay = y0 * p.a_stride + (p.shift_a ? p.dy[tap] : 0);
-        const int bx = x0 * p.b_stride + (p.shift_a ? 0 : p.dx[tap]), by = y0 * p.b_stride + (p.shift_a ? 0 : p.dy[tap]);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
+          const int ax = x0 * p.a_stride + (p.shift_a ? p.dx[tap] : 0), ay = y0 * p.a_stride + (p.shift_a ? p.dy[tap] : 0);
+          const int bx = x0 * p.b_stride + (p.shift_a ? 0 : p.dx[tap]), by = y0 * p.b_stride + (p.shift_a ? 0 : p.dy[tap]);
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, ax, ay, b);
+          for (int m = 0; m < 2; ++m)
+            tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, ax, ay, b);
 #pragma unroll
-        for (int n = 0; n < BLOCK_N / 64; ++n)
-          tma_load_4d(sa + kABytes + n * kChunkBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, bx, by, b);
+          for (int n = 0; n < BLOCK_N / 64; ++n)
+            tma_load_4d(sa + kABytes + n * kChunkBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, bx, by, b);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
@@ -136,13 +138,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const uint32_t sa = smem_base + stage * kStageBytes;
         const uint64_t adesc = umma_desc_mn_sw128(sa, kChunkBytes);
         const uint64_t bdesc = umma_desc_mn_sw128(sa + kABytes, kChunkBytes);
+        if (elect_one()) {            // ONE election per k-block: the body is straight-line UTCHMMA + commits
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // 16 pixel rows (2 KB) per MMA
-          umma_f16(tmem_base, adesc + 128u * k, bdesc + 128u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(empty_bar(stage));
+          for (int k = 0; k < 8; ++k)   // 16 pixel rows (2 KB) per MMA
+            umma_f16(tmem_base, adesc + 128u * k, bdesc + 128u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == n_kb - 1) umma_commit(done_bar);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done_bar);
+      if (n_kb == 0 && elect_one()) umma_commit(done_bar);
     }
     __syncwarp();
   } else if (n_kb > 0) {
@@ -259,7 +264,7 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   const int n_kb = (int)(kb_hi - kb_lo);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       int stage = 0;
       uint32_t phase = 0;
       const int tiles = p.tiles_x * p.tiles_y;
@@ -270,20 +275,22 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int x0 = tx * 8, y0 = ty * 16;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * kStageBytes;
-        mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + kBBytes));
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-          tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, x0, y0, b);
+          for (int m = 0; m < 2; ++m)
+            tma_load_4d(sa + m * kChunkBytes, &tmDY, full_bar(stage), co_t * 128 + m * 64, x0, y0, b);
 #pragma unroll
-        for (int n = 0; n < BLOCK_N / 64; ++n)
-          tma_load_4d(sa + kABytes + n * kW3SlabBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, x0 - 1,
-                      y0 + r - 1, b);
+          for (int n = 0; n < BLOCK_N / 64; ++n)
+            tma_load_4d(sa + kABytes + n * kW3SlabBytes, &tmX, full_bar(stage), ci_t * BLOCK_N + n * 64, x0 - 1,
+                        y0 + r - 1, b);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
@@ -291,20 +298,23 @@ wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         tc_fence_after();
         const uint32_t sa = smem_base + stage * kStageBytes;
         const uint32_t sb = sa + kABytes;
+        if (elect_one()) {            // ONE election per k-block: the body is straight-line UTCHMMA + commits
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
+          for (int s = 0; s < 3; ++s) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
-            const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, kChunkBytes);
-            const uint64_t bdesc =
-                umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j) * 1280u + (uint32_t)s * 128u, kW3SlabBytes, 1280u);
-            umma_f16(tmem_base + (uint32_t)(s * BLOCK_N), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
+              const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, kChunkBytes);
+              const uint64_t bdesc =
+                  umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j) * 1280u + (uint32_t)s * 128u, kW3SlabBytes, 1280u);
+              umma_f16(tmem_base + (uint32_t)(s * BLOCK_N), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar(stage));
+          if (kb == n_kb - 1) umma_commit(done_bar);
         }
-        umma_commit(empty_bar(stage));
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done_bar);
+      if (n_kb == 0 && elect_one()) umma_commit(done_bar);
     }
     __syncwarp();
   } else if (n_kb > 0) {
@@ -447,7 +457,7 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   const int n_kb = (int)(kb_hi - kb_lo);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       int stage = 0;
       uint32_t phase = 0;
       const int tiles = p.tiles_x * p.tiles_y;
@@ -458,15 +468,17 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         const int x0 = tx * 8, y0 = ty * 16 - 1;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * kC64StageBytes;
-        mbar_expect_tx(full_bar(stage), (uint32_t)(17 * 8 * 128 + 17 * 10 * 128));
-        tma_load_4d(sa, &tmDY, full_bar(stage), 0, x0, y0, b);
-        tma_load_4d(sa + kC64ABytes, &tmX, full_bar(stage), ci_t * 64, x0 - 1, y0, b);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), (uint32_t)(17 * 8 * 128 + 17 * 10 * 128));
+          tma_load_4d(sa, &tmDY, full_bar(stage), 0, x0, y0, b);
+          tma_load_4d(sa + kC64ABytes, &tmX, full_bar(stage), ci_t * 64, x0 - 1, y0, b);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
@@ -474,19 +486,22 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         tc_fence_after();
         const uint32_t sa = smem_base + stage * kC64StageBytes;
         const uint32_t sb = sa + kC64ABytes;
+        if (elect_one()) {            // ONE election per k-block: the body is straight-line UTCHMMA + commits
 #pragma unroll
-        for (int rho = 0; rho < 2; ++rho) {
+          for (int rho = 0; rho < 2; ++rho) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
-            const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, 1024u);
-            const uint64_t bdesc = umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j + rho) * 1280u, 128u, 1280u);
-            umma_f16(tmem_base + (uint32_t)(rho * 192), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
+              const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, 1024u);
+              const uint64_t bdesc = umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j + rho) * 1280u, 128u, 1280u);
+              umma_f16(tmem_base + (uint32_t)(rho * 192), adesc, bdesc, kIdesc, (kb | j) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar(stage));
+          if (kb == n_kb - 1) umma_commit(done_bar);
         }
-        umma_commit(empty_bar(stage));
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done_bar);
+      if (n_kb == 0 && elect_one()) umma_commit(done_bar);
     }
     __syncwarp();
   } else if (n_kb > 0) {

@@ -94,7 +94,7 @@ wgrad_first_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   const int tiles = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues (see elect_one in common.cuh)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -104,17 +104,21 @@ wgrad_first_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int is = it % kWfPatchStages;
         mbar_wait(in_empty(is), (uint32_t)(((it / kWfPatchStages) & 1) ^ 1));
-        mbar_expect_tx(in_full(is), kWfPatchBytes);
-        tma_load_4d(smem_in + is * kWfPatchStride, &tmX, in_full(is), tx * kWfTw - 4, ty * kWfTh - 1, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(in_full(is), kWfPatchBytes);
+          tma_load_4d(smem_in + is * kWfPatchStride, &tmX, in_full(is), tx * kWfTw - 4, ty * kWfTh - 1, 0, b);
+        }
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), (uint32_t)kWfChunk);
-        tma_load_4d(smem_ab + stage * 2 * kWfChunk, &tmDY, full_bar(stage), 0, tx * kWfTw, ty * kWfTh, b);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), (uint32_t)kWfChunk);
+          tma_load_4d(smem_ab + stage * 2 * kWfChunk, &tmDY, full_bar(stage), 0, tx * kWfTw, ty * kWfTh, b);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < n_kb; ++kb) {
@@ -125,13 +129,16 @@ wgrad_first_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         // address terms, so describe A starting AT the zero chunk instead: rows 0..63 <- zeros, rows 64..127 <- dY
         const uint64_t adesc = umma_desc_mn_sw128(smem_zero, sa - smem_zero);
         const uint64_t bdesc = umma_desc_mn_sw128(sa + kWfChunk, kWfChunk);
+        if (elect_one()) {            // ONE election per k-block: the body is straight-line UTCHMMA + commits
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // 16 pixel rows (2 KB) per MMA
-          umma_f16(tmem_base, adesc + 128u * k, bdesc + 128u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(empty_bar(stage));
+          for (int k = 0; k < 8; ++k)   // 16 pixel rows (2 KB) per MMA
+            umma_f16(tmem_base, adesc + 128u * k, bdesc + 128u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == n_kb - 1) umma_commit(done_bar);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(done_bar);
+      if (n_kb == 0 && elect_one()) umma_commit(done_bar);
     }
     __syncwarp();
   } else {
