@@ -68,7 +68,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // SPLIT = 1: 4 epilogue warps, each thread handles all 64 columns of a chunk.  SPLIT = 2: 8 epilogue warps, two
 // per TMEM lane quarter, each thread handles 32 of the 64 columns (`hsel`) -- halves the per-tile epilogue latency
 // for the narrow layers where the epilogue, not the MMA, paces the tile.
-template <int BLOCK_N, int SPLIT = 1>
+// CLUSTER_ARRIVE: `tempty_bar_addr` is a shared::cluster address (the leader CTA's barrier of a cta_group::2 pair,
+// see conv_rs2.cu) and the accumulator hand-back is a cluster-scope arrive.
+// PLAIN: the launch has no residual / fp32 stream / gate / out_scale / colsum / absmax (every inference layer of the
+// vgg networks): those options compile away -- the epilogue of the 64-channel layers paces the kernel (two warps
+// per scheduler, one dependent chain per tile), so every runtime test on the chain counts.
+template <int BLOCK_N, int SPLIT = 1, bool CLUSTER_ARRIVE = false, bool PLAIN = false>
 __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
@@ -87,12 +92,16 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   const __half* res_row = nullptr;
   const float* res32_row = nullptr;
   float* y32_row = nullptr;
-  const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
-  if (p.residual != nullptr && valid) res_row = p.residual + row_off;
-  if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
-  if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
-  const __half* gate_row = (p.gate != nullptr && valid) ? p.gate + row_off : nullptr;
-  const float out_scale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.0f;
+  const __half* gate_row = nullptr;
+  float out_scale = 1.0f;
+  if constexpr (!PLAIN) {
+    const size_t row_off = ((size_t)((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout_pad + n * BLOCK_N;
+    if (p.residual != nullptr && valid) res_row = p.residual + row_off;
+    if (p.residual_f32 != nullptr && valid) res32_row = p.residual_f32 + row_off;
+    if (p.y_f32 != nullptr && valid) y32_row = p.y_f32 + row_off;
+    gate_row = (p.gate != nullptr && valid) ? p.gate + row_off : nullptr;
+    out_scale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.0f;
+  }
   const bool shfl_pool = p.pool && (p.tw == 8 || p.tw == 16);
   const bool write_full = !p.pool || p.store_full || !shfl_pool;
 #pragma unroll 1
@@ -129,7 +138,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
           f[i + 3] = __uint_as_float(v[i + 3]) + b3;
         }
       }
-      if (res_row != nullptr) {
+      if (!PLAIN && res_row != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + c * 64 + h * 32 + i));
@@ -142,7 +151,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
           }
         }
       }
-      if (res32_row != nullptr) {
+      if (!PLAIN && res32_row != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
@@ -153,7 +162,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
       }
-      if (p.gate != nullptr) {
+      if (!PLAIN && p.gate != nullptr) {
         // data gradient leaving through the previous layer's ReLU: keep it where that layer's output was > 0
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -167,16 +176,16 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
             f[i + 2 * j + 1] = gf.y > 0.0f ? f[i + 2 * j + 1] * out_scale : 0.0f;
           }
         }
-      } else if (p.out_scale != nullptr) {
+      } else if (!PLAIN && p.out_scale != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] *= out_scale;
       }
-      if (y32_row != nullptr) {
+      if (!PLAIN && y32_row != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
       }
-      if (p.colsum != nullptr) {
+      if (!PLAIN && p.colsum != nullptr) {
         // column sums over the warp's 32 rows by a halving butterfly (31 shuffles): lane i ends up with column i
         float r[32];
 #pragma unroll
@@ -194,7 +203,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
         if (p.n_tiles == 1) csum[c * 2 + h] += r[0];       // single channel tile: accumulate across the CTA's tiles
         else atomicAdd(p.colsum + n * BLOCK_N + c * 64 + h * 32 + lane, r[0]);
       }
-      if (p.absmax != nullptr) {
+      if (!PLAIN && p.absmax != nullptr) {
         float m = 0.0f;
         if (valid) {
 #pragma unroll
@@ -213,7 +222,9 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp right away
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar_addr);
+      if (lane == 0) {
+        if (CLUSTER_ARRIVE) mbar_arrive_cluster(tempty_bar_addr); else mbar_arrive(tempty_bar_addr);
+      }
     }
     // (bulk-store bookkeeping by ONE lane of the first epilogue warp: elect.sync picks the same lane every time, and
     //  issued from warp-uniform control flow the TMA instructions need no per-instruction election loop)

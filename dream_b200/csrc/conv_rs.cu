@@ -50,7 +50,7 @@ constexpr int kRsThreads = 64 + 128 * kRsEpiSplit;
 
 // HEAD    : the network head -- BLOCK_N = 16 accumulator columns of which the first cout_real are channels, written as
 //           fp32 NCHW straight from the accumulators (no staging, no TMA store); resident weights only.
-template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO, bool HEAD = false>
+template <int BLOCK_N, bool RESIDENT, int SUBTILES, bool HALO, bool HEAD = false, bool PLAIN = false>
 __global__ void __launch_bounds__(kRsThreads, 1)
 conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
@@ -282,7 +282,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool valid = (ox < p.Wo) && (oy < p.Ho);
         const uint32_t t_row =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
-        epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+        epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit, false, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                  tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid,
                                                  chunk_ctr, hsel, csum, bias_regs ? breg : nullptr);
       }
@@ -394,11 +394,17 @@ static int launch_rs(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t es[4] = {1, 1, 1, 1};
     if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "rs output")) return -1;
   }
-  auto kern = conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO, HEAD>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // PLAIN: none of the optional epilogue inputs / outputs (see epilogue_nhwc_tile)
+  // (measured, B=128: PLAIN is 10 % faster for the resident 64 -> 128 kernel, 1-5 % for the 64-channel ones, and 8 %
+  //  SLOWER for the streamed 128-channel pair kernel -- a code-generation effect; that variant keeps the generic epilogue)
+  const bool plain = !HEAD && !(BLOCK_N == 128 && !RESIDENT) && d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
+                     d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
+  auto kern = plain ? conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO, HEAD, !HEAD>
+                    : conv_rs_kernel<BLOCK_N, RESIDENT, SUBTILES, HALO, HEAD, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[plain]) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    attr_set[plain] = true;
   }
   const int sms = device_sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;

@@ -1,0 +1,387 @@
+// conv_rs2.cu -- CTA-pair (tcgen05 cta_group::2) variant of the row-shared 3x3 kernel (conv_rs.cu) for the layers
+// with 64 / 128 output channels.
+//
+// Why: with N = 64 or 128 accumulator columns the single-CTA MMA is bound by SHARED-MEMORY bandwidth, not by the
+// tensor pipe (ncu, conv_rs<64>: l1tex data pipe 76 % busy, 1728 tensor-core wavefronts per tile = 36 MMAs x
+// (32 for the 128x16 A slice + 16 for the 64x16 B slice) against 32 math cycles per MMA).  A CTA pair runs ONE
+// M = 256 MMA over two output tiles: each CTA supplies its own 128 A rows (its slab) and only HALF of the B tile
+// (N/2 output channels), so per CTA and MMA the tensor core reads 32 + 8 (N = 64) or 32 + 16 (N = 128) wavefronts,
+// and each CTA loads / stores only half of every weight tile.
+//
+// Pair protocol (rank 0 = leader):
+//   * both CTAs run the same tile sequence; rank r owns output tile row 2*typ + r of pair-tile typ;
+//   * TMA loads land in the executing CTA's shared memory but count their bytes on the LEADER's full barrier
+//     (cp.async.bulk.tensor ... cta_group::2, barrier address mapped with mapa); the leader expects both halves;
+//   * the leader's elected lane issues tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster arrives on the
+//     empty / accumulator-full barriers of BOTH CTAs;
+//   * each CTA's epilogue drains its own TMEM half and hands the accumulator stage back with a cluster-scope
+//     arrive on the leader's barrier (count = both CTAs' epilogue warps).
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "dreamb200.h"
+
+#include <stdlib.h>
+
+namespace db200 {
+
+int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride,
+                        const char* what);
+int device_sm_count();
+
+constexpr int kR2Tw = 8, kR2Th = 16;
+constexpr int kR2EpiSplit = 2;
+constexpr int kR2Threads = 64 + 128 * kR2EpiSplit;
+constexpr int kR2Rows = kR2Th + 2;                                       // image rows per slab
+constexpr int kR2Pitch = 1280;                                           // 10 pixels x 128 B
+constexpr int kR2SlabTx = kR2Rows * kR2Pitch;
+constexpr int kR2SlabBytes = ((kR2SlabTx + 1023) / 1024) * 1024;
+
+struct Rs2Extra {
+  int sa, sb;        // ring depths: activation slabs, weight half-tiles (streamed mode)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo2(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BLOCK_N, bool RESIDENT, bool PLAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kR2Threads, 1)
+conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+                const __grid_constant__ ConvParams p, const __grid_constant__ Rs2Extra x) {
+  constexpr int kBHalf = (BLOCK_N / 2) * 128;                            // this CTA's half of a weight tile
+  constexpr int kTmemCols = 2 * BLOCK_N;                                 // 128 or 256
+  constexpr uint32_t kIdesc = umma_idesc_f16_m256(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int sa = x.sa, sb = x.sb;
+  const int n_wtiles = 9 * p.kchunks;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + sa * kR2SlabBytes;
+  const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : sb) * kBHalf;
+  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
+  const uint32_t bar_base = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (sa + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * sa + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * sa + sb + s); };
+  const uint32_t misc = bar_base + 8u * (2 * sa + 2 * sb);
+  auto tfull_bar = [&](int a) { return misc + 8u * a; };
+  auto tempty_bar = [&](int a) { return misc + 16u + 8u * a; };
+  const uint32_t wbar = misc + 32u;
+  const uint32_t tmem_ptr_smem = misc + 40u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  const uint32_t smem_bias = misc + 64u;
+  float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
+  stage_bias(p, smem_bias_gen, BLOCK_N);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.pool) tma_prefetch_desc(&tmP);
+    for (int s = 0; s < sa; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kR2EpiSplit); }
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes are counted on the leader's barriers) =====================
+    if (RESIDENT) {
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(wbar, (uint32_t)(2 * n_wtiles * kBHalf));
+        const uint32_t wbar_l = mapa_cluster(wbar, 0);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_3d_2sm(smem_b + (tap * p.kchunks + kc) * kBHalf, &tmB, wbar_l, kc * 64,
+                            (int)rank * (BLOCK_N / 2), tap);
+      }
+      __syncwarp();
+    }
+    int as_ = 0, bs_ = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+      int n, tx, typ, b;
+      decode_tile(p, tile, n, tx, typ, b);
+      const int x0 = tx * kR2Tw, y0 = (typ * 2 + (int)rank) * kR2Th;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(aempty(as_), aph ^ 1u);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(afull(as_), (uint32_t)(2 * kR2SlabTx));
+          tma_load_4d_2sm(smem_a + as_ * kR2SlabBytes, &tmA, mapa_cluster(afull(as_), 0), kc * 64, x0 - 1, y0 - 1, b);
+        }
+        if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+        if (!RESIDENT) {
+          for (int t = 0; t < 9; ++t) {           // weight tiles in the order the MMA loop consumes them: s outer, r inner
+            const int s = t / 3, r = t - s * 3;
+            mbar_wait(bempty(bs_), bph ^ 1u);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(bfull(bs_), (uint32_t)(2 * kBHalf));
+              tma_load_3d_2sm(smem_b + bs_ * kBHalf, &tmB, mapa_cluster(bfull(bs_), 0), kc * 64,
+                              (int)rank * (BLOCK_N / 2), r * 3 + s);
+            }
+            if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only; whole warp, one elected lane) =====================
+    if (rank == 0) {
+      if (RESIDENT) mbar_wait(wbar, 0);
+      int as_ = 0, bs_ = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t accph = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar(acc), accph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const bool last_kc = kc == p.kchunks - 1;
+          mbar_wait(afull(as_), aph);
+          tc_fence_after();
+          const uint32_t slab = smem_a + as_ * kR2SlabBytes;
+          if (RESIDENT) {
+            if (elect_one()) {
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                  const uint64_t bdesc = umma_desc_k_sw128(smem_b + ((r * 3 + s) * p.kchunks + kc) * kBHalf);
+                  const uint64_t adesc =
+                      umma_desc_k_sw128_sbo2(slab + (uint32_t)(r * kR2Pitch) + (uint32_t)s * 128u, kR2Pitch);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kc | s | r | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit_2sm(aempty(as_));
+              if (last_kc) umma_commit_2sm(tfull_bar(acc));
+            }
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < 9; ++t) {
+              const int s = t / 3, r = t - s * 3;
+              mbar_wait(bfull(bs_), bph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t bdesc = umma_desc_k_sw128(smem_b + bs_ * kBHalf);
+                const uint64_t adesc =
+                    umma_desc_k_sw128_sbo2(slab + (uint32_t)(r * kR2Pitch) + (uint32_t)s * 128u, kR2Pitch);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kc | t | k) != 0 ? 1u : 0u);
+                umma_commit_2sm(bempty(bs_));
+                if (t == 8) umma_commit_2sm(aempty(as_));
+                if (t == 8 && last_kc) umma_commit_2sm(tfull_bar(acc));
+              }
+              if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
+            }
+          }
+          if (++as_ == sa) { as_ = 0; aph ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) accph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs drain their own TMEM half) =====================
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    const int ly = row / kR2Tw, lx = row - ly * kR2Tw;
+    int acc = 0;
+    uint32_t accph = 0;
+    uint32_t chunk_ctr = 0;
+    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float breg[32];
+    const bool bias_regs = BLOCK_N == 64 && p.bias != nullptr;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) breg[i] = bias_regs ? __ldg(p.bias + hsel * 32 + i) : 0.0f;
+    const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
+    for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+      int n, tx, typ, b;
+      decode_tile(p, tile, n, tx, typ, b);
+      const int ty = typ * 2 + (int)rank;
+      mbar_wait(tfull_bar(acc), accph);
+      tc_fence_after();
+      const int ox = tx * kR2Tw + lx, oy = ty * kR2Th + ly;
+      const bool valid = (ox < p.Wo) && (oy < p.Ho);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      epilogue_nhwc_tile<BLOCK_N, kR2EpiSplit, true, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+                                                     acc ? tempty_l1 : tempty_l0, 0, tx, ty, b, ox, oy, valid, row, lane,
+                                                     epi_tid, chunk_ctr, hsel, csum, bias_regs ? breg : nullptr);
+      acc ^= 1;
+      if (acc == 0) accph ^= 1u;
+    }
+    flush_colsum<BLOCK_N, kR2EpiSplit>(p, csum, lane, hsel);
+    if (epi_tid < 32) {
+      if (elect_one()) tma_store_wait_read<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // nobody leaves (or frees TMEM) while the peer may still signal / be signalled
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, bool RESIDENT>
+static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = kR2Tw; p.th = kR2Th;
+  p.tiles_x = (d->Wo + kR2Tw - 1) / kR2Tw;
+  p.tiles_y = (d->Ho + 2 * kR2Th - 1) / (2 * kR2Th);                  // PAIRS of 16-row tiles
+  p.n_tiles = 1;
+  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->B;
+  DB_REQUIRE((long long)p.tiles_x * p.tiles_y * d->B < (1ll << 24) && p.tiles_x < 65536 && p.tiles_y < 65536,
+             "conv: too many tiles for one launch (%d x %d x %d)", p.tiles_x, p.tiles_y, d->B);
+  p.absmax = d->absmax;
+  p.gate = reinterpret_cast<const __half*>(d->gate);
+  p.out_scale = d->out_scale;
+  p.colsum = d->colsum;
+  p.mg_n = div_magic(1);
+  p.mg_x = div_magic(p.tiles_x);
+  p.mg_y = div_magic(p.tiles_y);
+  p.in_stride = 1;
+  p.taps = 9;
+  p.kchunks = d->Cin / 64;
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.residual_f32 = d->residual_f32;
+  p.y_f32 = d->y_f32;
+  p.Cout_pad = d->Cout_pad;
+  p.relu = d->relu;
+  p.pool = d->y_pool != nullptr ? 1 : 0;
+  p.store_full = d->y != nullptr ? 1 : 0;
+
+  constexpr int kBHalf = (BLOCK_N / 2) * 128;
+  const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
+  Rs2Extra x;
+  int budget = 232448 - 1024 - out_bytes - 1024 - BLOCK_N * 4;
+  if (RESIDENT) {
+    budget -= 9 * p.kchunks * kBHalf;
+    x.sa = budget / kR2SlabBytes;
+    if (x.sa > 6) x.sa = 6;
+    x.sb = 1;
+  } else {
+    x.sa = 3;
+    x.sb = (budget - x.sa * kR2SlabBytes) / kBHalf;
+    if (x.sb > 18) x.sb = 18;
+  }
+  DB_REQUIRE(x.sa >= 2 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs2: shared memory budget too small");
+  const int smem_bytes =
+      1024 + x.sa * kR2SlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBHalf + out_bytes + 1024 + BLOCK_N * 4;
+
+  CUtensorMap tmA, tmB, tmC, tmP;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmP, 0, sizeof(tmP));
+  const uint32_t es4[4] = {1, 1, 1, 1};
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+    uint32_t box[4] = {64, 10u, (uint32_t)kR2Rows, 1};
+    if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es4, "rs2 activation")) return -1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, 9};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {64, (uint32_t)(BLOCK_N / 2), 1};
+    uint32_t es[3] = {1, 1, 1};
+    if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "rs2 weights")) return -1;
+  }
+  if (d->y_pool != nullptr) {
+    const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, Wp, Hp, (uint64_t)d->B};
+    uint64_t str[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+    uint32_t box[4] = {64, kR2Tw / 2, kR2Th / 2, 1};
+    if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es4, "rs2 pooled output")) return -1;
+  }
+  if (d->y != nullptr) {
+    uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
+    uint32_t box[4] = {64, kR2Tw, kR2Th, 1};
+    if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es4, "rs2 output")) return -1;
+  }
+  const bool plain = d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
+                     d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
+  auto kern = plain ? conv_rs2_kernel<BLOCK_N, RESIDENT, true> : conv_rs2_kernel<BLOCK_N, RESIDENT, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[plain]) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[plain] = true;
+  }
+  const int sms = device_sm_count() & ~1;
+  int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
+  kern<<<grid, kR2Threads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p, x);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Returns 1 and launches when the layer qualifies for the CTA-pair kernel, 0 otherwise, <0 on error.
+int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  static int mode = -1;
+  if (mode < 0) {
+    // bit 0: 64 -> 64 channels, bit 1: 128 output channels, bit 2: other 64-output-channel layers.  Measured at B = 128:
+    // 64 -> 64 @400x400 + pool 1.47 -> 1.32 ms; 64 -> 128 unchanged; 128 -> 128 @200x200 slower (1.44 -> 1.60 ms: there the
+    // epilogue of the pair, not shared memory, paces the tile) -- so only bit 0 is on by default.
+    const char* e = getenv("DREAMB200_RS2");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0) return 0;
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->taps != 9 || d->in_stride != 1) return 0;
+  if (d->Ho != d->H || d->Wo != d->W) return 0;
+  if (d->Cout_pad != 64 && d->Cout_pad != 128) return 0;
+  if (d->Ho < 2 * kR2Th) return 0;
+  for (int t = 0; t < 9; ++t)
+    if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1) return 0;
+  const double util = (double)d->Wo * d->Ho /
+                      ((double)((d->Wo + kR2Tw - 1) / kR2Tw) * ((d->Ho + 2 * kR2Th - 1) / (2 * kR2Th)) * 256.0);
+  if (util < 0.8) return 0;
+  const int kchunks = d->Cin / 64;
+  // resident half tiles need room for at least two activation slabs next to them
+  const int out_bytes = 2 * kStageOutBytes + (d->y_pool != nullptr ? 2 * kPoolBytes : 0);
+  const int resident_bytes = 9 * kchunks * (d->Cout_pad / 2) * 128;
+  const bool resident = 232448 - 1024 - out_bytes - 1024 - d->Cout_pad * 4 - resident_bytes >= 2 * kR2SlabBytes;
+  int rc;
+  if (d->Cout_pad == 64) {
+    if (kchunks == 1 && !(mode & 1)) return 0;
+    if (kchunks > 1 && !(mode & 4)) return 0;
+    rc = resident ? launch_rs2<64, true>(d, stream) : launch_rs2<64, false>(d, stream);
+  } else {
+    if (!(mode & 2)) return 0;
+    rc = resident ? launch_rs2<128, true>(d, stream) : launch_rs2<128, false>(d, stream);
+  }
+  return rc == 0 ? 1 : rc;
+}
+
+}  // namespace db200

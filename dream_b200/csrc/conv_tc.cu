@@ -29,7 +29,7 @@ template <int OUT_MODE>
 __host__ __device__ constexpr int kTcThreads() { return OUT_MODE == DREAMB200_OUT_NHWC_F16 ? 64 + 256 : 64 + 128; }
 constexpr int kTcSplit = 2;
 
-template <int BLOCK_N, int OUT_MODE>
+template <int BLOCK_N, int OUT_MODE, bool PLAIN = false>
 __global__ void __launch_bounds__(kTcThreads<OUT_MODE>(), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
@@ -170,7 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
-        epilogue_nhwc_tile<BLOCK_N, kTcSplit>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+        epilogue_nhwc_tile<BLOCK_N, kTcSplit, false, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                               tempty_bar(as), n, tx, ty, b, ox, oy, valid, row, lane, epi_tid,
                                               chunk_ctr, hsel, csum);
       } else {
@@ -286,6 +286,7 @@ static double choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out,
 
 int device_sm_count();
 int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream);   // conv_rs.cu
+int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_rs2.cu
 
 template <int BLOCK_N, int OUT_MODE>
 static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
@@ -371,11 +372,14 @@ static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms
     if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es, "output")) return -1;
   }
 
-  auto kern = conv_tc_kernel<BLOCK_N, OUT_MODE>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  constexpr bool kNhwc = OUT_MODE == DREAMB200_OUT_NHWC_F16;
+  const bool plain = kNhwc && d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
+                     d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
+  auto kern = plain ? conv_tc_kernel<BLOCK_N, OUT_MODE, kNhwc> : conv_tc_kernel<BLOCK_N, OUT_MODE, false>;
+  static bool attr_set[2] = {false, false};  // per template instantiation
+  if (!attr_set[plain]) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    attr_set[plain] = true;
   }
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   kern<<<grid, kTcThreads<OUT_MODE>(), smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
@@ -435,7 +439,9 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
   DB_REQUIRE((d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0,
              "conv: output strides must be multiples of 16 bytes");
   {
-    const int r = try_conv_rs(d, stream);      // row-shared kernel for the narrow 3x3 layers
+    int r = try_conv_rs2(d, stream);           // CTA-pair slab kernel (opt-in: DREAMB200_RS2)
+    if (r != 0) return r > 0 ? 0 : r;
+    r = try_conv_rs(d, stream);                // row-shared kernel for the narrow 3x3 layers
     if (r != 0) return r > 0 ? 0 : r;
   }
   if (d->Cout_pad % 256 == 0) return launch<256, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
