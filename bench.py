@@ -275,7 +275,10 @@ def main():
     ms, launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.finish() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
-    ms_e2e, _ = timed(run_e2e, args.steps, args.warmup, whole=True)
+    # e2e crosses PCIe and the host: on shared boxes single runs scatter (observed 4.6k .. 7.5k img/s for the same
+    # build), so K steps are timed three times and the median run is reported
+    e2e_runs = sorted(timed(run_e2e, args.steps, args.warmup if i == 0 else 1, whole=True)[0] for i in range(3))
+    ms_e2e = e2e_runs[1]
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- instrumented pass: per-launch CUDA-event durations of the tensor-core conv kernels ----
@@ -355,7 +358,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W * 4 + (B * K_KP * out_h * out_w * 4 if mode == "train" else 0),
                     "d2h_bytes_per_step": 4 if mode == "train" else B * K_KP * 2 * 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "runs_ms_per_step": [t / args.steps for t in e2e_runs], "reported": "median of 3 runs of K steps"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

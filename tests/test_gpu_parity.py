@@ -361,3 +361,18 @@ def test_facade_single_image_and_checkpoint_round_trip(tmp_path, built_lib):
     net2.enable_evaluation()
     res2 = net2.keypoints_from_image(img)
     assert np.array_equal(res["detected_keypoints"], res2["detected_keypoints"])
+
+
+@pytest.mark.gpu
+def test_pair_kernel_is_bit_identical_to_single_cta_kernel(built_lib):
+    """conv_rs2 (tcgen05 cta_group::2 CTA pair, conv_rs2.cu) against conv_rs on the same inputs: same MMA K order,
+    same epilogue, so the outputs must agree bit for bit (64 -> 64 with / without the fused pool, odd tile counts,
+    128 output channels through the opt-in mask).  Each side runs in its own process (tools/rs2_check.py): the
+    kernel choice is read once per process from DREAMB200_RS2."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "rs2_check.py"), "s64_64_40x56_pool",
+                        "s64_64_100_both", "s128_128_48_pool"], capture_output=True, text=True, timeout=300)
+    assert "ALL IDENTICAL" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
