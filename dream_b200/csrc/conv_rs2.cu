@@ -67,7 +67,7 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n_wtiles = 9 * p.kchunks;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + sa * kR2SlabBytes;
-  const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : sb) * kBHalf;
+  const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : 3 * sb) * kBHalf;      // sb counts GROUPS of 3 tiles
   const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
   const uint32_t bar_base = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
   auto afull = [&](int s) { return bar_base + 8u * s; };
@@ -132,13 +132,17 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (++as_ == sa) { as_ = 0; aph ^= 1u; }
         if (!RESIDENT) {
-          for (int t = 0; t < 9; ++t) {           // weight tiles in the order the MMA loop consumes them: s outer, r inner
-            const int s = t / 3, r = t - s * 3;
+          // streamed weights travel in GROUPS of three half tiles (the vertical taps r = 0..2 of one horizontal tap
+          // s) per barrier: with one tile per barrier the wait / elect / commit overhead of the issuing warp (~300
+          // cycles) was paid per 4 MMAs and paced the 128-channel kernel
+          for (int s = 0; s < 3; ++s) {
             mbar_wait(bempty(bs_), bph ^ 1u);
             if (elect_one()) {
-              if (rank == 0) mbar_expect_tx(bfull(bs_), (uint32_t)(2 * kBHalf));
-              tma_load_3d_2sm(smem_b + bs_ * kBHalf, &tmB, mapa_cluster(bfull(bs_), 0), kc * 64,
-                              (int)rank * (BLOCK_N / 2), r * 3 + s);
+              if (rank == 0) mbar_expect_tx(bfull(bs_), (uint32_t)(2 * 3 * kBHalf));
+              const uint32_t bar = mapa_cluster(bfull(bs_), 0);
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                tma_load_3d_2sm(smem_b + (bs_ * 3 + r) * kBHalf, &tmB, bar, kc * 64, (int)rank * (BLOCK_N / 2), r * 3 + s);
             }
             if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
           }
@@ -182,20 +186,22 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           } else {
 #pragma unroll 1
-            for (int t = 0; t < 9; ++t) {
-              const int s = t / 3, r = t - s * 3;
+            for (int s = 0; s < 3; ++s) {
               mbar_wait(bfull(bs_), bph);
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t bdesc = umma_desc_k_sw128(smem_b + bs_ * kBHalf);
-                const uint64_t adesc =
-                    umma_desc_k_sw128_sbo2(slab + (uint32_t)(r * kR2Pitch) + (uint32_t)s * 128u, kR2Pitch);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kc | t | k) != 0 ? 1u : 0u);
+                for (int r = 0; r < 3; ++r) {
+                  const uint64_t bdesc = umma_desc_k_sw128(smem_b + (bs_ * 3 + r) * kBHalf);
+                  const uint64_t adesc =
+                      umma_desc_k_sw128_sbo2(slab + (uint32_t)(r * kR2Pitch) + (uint32_t)s * 128u, kR2Pitch);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kc | s | r | k) != 0 ? 1u : 0u);
+                }
                 umma_commit_2sm(bempty(bs_));
-                if (t == 8) umma_commit_2sm(aempty(as_));
-                if (t == 8 && last_kc) umma_commit_2sm(tfull_bar(acc));
+                if (s == 2) umma_commit_2sm(aempty(as_));
+                if (s == 2 && last_kc) umma_commit_2sm(tfull_bar(acc));
               }
               if (++bs_ == sb) { bs_ = 0; bph ^= 1u; }
             }
@@ -294,12 +300,12 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     x.sb = 1;
   } else {
     x.sa = 3;
-    x.sb = (budget - x.sa * kR2SlabBytes) / kBHalf;
-    if (x.sb > 18) x.sb = 18;
+    x.sb = (budget - x.sa * kR2SlabBytes) / (3 * kBHalf);              // groups of three half tiles
+    if (x.sb > 6) x.sb = 6;
   }
-  DB_REQUIRE(x.sa >= 2 && x.sb >= 1 && (RESIDENT || x.sb >= 3), "conv_rs2: shared memory budget too small");
+  DB_REQUIRE(x.sa >= 2 && x.sb >= 1 && (RESIDENT || x.sb >= 2), "conv_rs2: shared memory budget too small");
   const int smem_bytes =
-      1024 + x.sa * kR2SlabBytes + (RESIDENT ? 9 * p.kchunks : x.sb) * kBHalf + out_bytes + 1024 + BLOCK_N * 4;
+      1024 + x.sa * kR2SlabBytes + (RESIDENT ? 9 * p.kchunks : 3 * x.sb) * kBHalf + out_bytes + 1024 + BLOCK_N * 4;
 
   CUtensorMap tmA, tmB, tmC, tmP;
   memset(&tmC, 0, sizeof(tmC));
@@ -351,11 +357,13 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
 int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   static int mode = -1;
   if (mode < 0) {
-    // bit 0: 64 -> 64 channels, bit 1: 128 output channels, bit 2: other 64-output-channel layers.  Measured at B = 128:
-    // 64 -> 64 @400x400 + pool 1.47 -> 1.32 ms; 64 -> 128 unchanged; 128 -> 128 @200x200 slower (1.44 -> 1.60 ms: there the
-    // epilogue of the pair, not shared memory, paces the tile) -- so only bit 0 is on by default.
+    // bit 0: 64 -> 64 channels, bit 1: 128 output channels with streamed weights (Cin >= 128), bit 2: other
+    // 64-output-channel layers, bit 3: 64 -> 128 (resident).  Measured at B = 128 (tools/rs2_check.py, same box):
+    // 64 -> 64 @400x400 + pool 1.47 -> 1.31 ms; 128 -> 128 @200x200 + pool 1.34 -> 1.07 ms (weights in groups of three
+    // tiles per barrier; one tile per barrier was SLOWER than conv_rs, 1.60 ms); 64 -> 128 unchanged (0.58 ms) -- so
+    // bits 0 and 1 are on by default.
     const char* e = getenv("DREAMB200_RS2");
-    mode = e ? atoi(e) : 1;
+    mode = e ? atoi(e) : 3;
   }
   if (mode == 0) return 0;
   if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->taps != 9 || d->in_stride != 1) return 0;
@@ -378,7 +386,7 @@ int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     if (kchunks > 1 && !(mode & 4)) return 0;
     rc = resident ? launch_rs2<64, true>(d, stream) : launch_rs2<64, false>(d, stream);
   } else {
-    if (!(mode & 2)) return 0;
+    if (kchunks == 1 ? !(mode & 8) : !(mode & 2)) return 0;
     rc = resident ? launch_rs2<128, true>(d, stream) : launch_rs2<128, false>(d, stream);
   }
   return rc == 0 ? 1 : rc;
