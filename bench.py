@@ -155,8 +155,10 @@ def run_reference(args):
         "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DREAM-vgg-Q inference (forward + peak extraction), 400x400, 7 keypoints",
-                   "sample": "%d frames per step on the host CPU" % n},
+        "config": {"workload": "DREAM-vgg-Q inference (forward + peak extraction), batch %d/GPU, %dx%d, 7 keypoints"
+                               % (B_PER_GPU, W, H),
+                   "parallelism": "host CPU, %d threads (rank 0 only)" % thr,
+                   "sample": "%d of the %d frames per step on the host CPU" % (n, B_PER_GPU)},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": thr, "kind": "port",
                          "sample": "%d steps x %d frames, oracle port of dream/models.py + image_proc peaks" %
                                    (len(times), n)},
