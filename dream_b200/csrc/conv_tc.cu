@@ -284,7 +284,12 @@ static double choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out,
   return best;
 }
 
+double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, int* th_out) {   // for conv_tc2.cu
+  return choose_tile(Wo, Ho, in_stride, even, tw_out, th_out);
+}
+
 int device_sm_count();
+int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_tc2.cu (opt-in)
 int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream);   // conv_rs.cu
 int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_rs2.cu
 
@@ -439,7 +444,9 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
   DB_REQUIRE((d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0,
              "conv: output strides must be multiples of 16 bytes");
   {
-    int r = try_conv_rs2(d, stream);           // CTA-pair slab kernel (opt-in: DREAMB200_RS2)
+    int r = try_conv_tc2(d, stream);           // CTA-pair kernel for the wide layers (opt-in: DREAMB200_TC2=1)
+    if (r != 0) return r > 0 ? 0 : r;
+    r = try_conv_rs2(d, stream);               // CTA-pair slab kernel (DREAMB200_RS2 bit mask)
     if (r != 0) return r > 0 ? 0 : r;
     r = try_conv_rs(d, stream);                // row-shared kernel for the narrow 3x3 layers
     if (r != 0) return r > 0 ? 0 : r;

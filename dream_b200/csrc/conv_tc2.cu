@@ -1,0 +1,293 @@
+// conv_tc2.cu -- CTA-pair (tcgen05 cta_group::2) variant of the generic tap-sum convolution (conv_tc.cu) for the wide
+// layers (Cout % 256 == 0).  OPT-IN (DREAMB200_TC2=1) and NOT YET VALIDATED ON A GPU: written at the end of round 1
+// after the GPU budget was spent; tools/tc2_check.py is its bring-up harness (bit-identity against conv_tc).
+//
+// Why: the wide layers run with the tensor pipe 90-95 % active at the 1000 W power cap (SM clock 1.35 GHz), i.e. their
+// rate is set by energy per FLOP.  In a pair each CTA fetches only HALF of every weight tile: per k-block 16 KB (A) +
+// 16 KB (B/2) instead of 16 + 32 KB cross the L2 -> SM fabric and are written to / read from shared memory (tensor-core
+// operand reads per MMA: 32 + 32 wavefronts instead of 32 + 64) -- a third less operand traffic for the same math.
+//
+// Pair protocol = conv_rs2.cu's: both CTAs run the same pair-tile sequence (rank r owns M-tile 2*mp + r of the same
+// output-channel tile n); TMA loads count their bytes on the LEADER's full barrier; the leader's elected lane issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256); tcgen05.commit multicast arrives on both CTAs' empty / accumulator-full
+// barriers; each CTA drains its own TMEM half and returns the stage with an arrive on the leader's barrier.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "dreamb200.h"
+
+#include <stdlib.h>
+
+namespace db200 {
+
+int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride,
+                        const char* what);
+int device_sm_count();
+double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, int* th_out);   // conv_tc.cu
+
+constexpr int kT2Split = 2;
+constexpr int kT2Threads = 64 + 128 * kT2Split;
+constexpr int kT2N = 256;
+constexpr int kT2BHalf = (kT2N / 2) * 128;                 // this CTA's half of a weight tile: 128 rows x 128 B
+constexpr int kT2StageBytes = kABytes + kT2BHalf;          // 32 KB
+
+template <bool PLAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+                const __grid_constant__ ConvParams p) {
+  constexpr uint32_t kIdesc = umma_idesc_f16_m256(kT2N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t smem_ab = smem_base;
+  const uint32_t smem_out = smem_ab + stages * kT2StageBytes;
+  const uint32_t out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
+  const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
+  const uint32_t bar_base = smem_out + out_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+  const uint32_t smem_bias = bar_base + 256u;
+  float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
+  stage_bias(p, smem_bias_gen, kT2N);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.pool) tma_prefetch_desc(&tmP);
+    for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kT2Split); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int num_kb = p.taps * p.kchunks;
+
+  // pair-tile q -> output-channel tile n (fastest) and M-tile m = 2 * (q / n_tiles) + rank -> (tx, ty, b); an odd
+  // M-tile count leaves the last pair's second tile at b == B: its loads are TMA zero fill, its stores clip away
+  auto decode = [&](int q, int& n, int& tx, int& ty, int& b) {
+    const int t = fast_div(q, p.mg_n);
+    n = q - t * p.n_tiles;
+    const int m = 2 * t + (int)rank;
+    const int t2 = fast_div(m, p.mg_x);
+    tx = m - t2 * p.tiles_x;
+    b = fast_div(t2, p.mg_y);
+    ty = t2 - b * p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes are counted on the leader's barriers) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int q = pair; q < p.total_tiles; q += n_pairs) {
+      int n, tx, ty, b;
+      decode(q, n, tx, ty, b);
+      const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int xi = x0 + p.dx[tap], yi = y0 + p.dy[tap];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_ab + stage * kT2StageBytes;
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), (uint32_t)(2 * (p.tw * p.th * 128 + kT2BHalf)));
+            const uint32_t bar = mapa_cluster(full_bar(stage), 0);
+            tma_load_4d_2sm(sa, &tmA, bar, kc * 64, xi, yi, b);
+            tma_load_3d_2sm(sa + kABytes, &tmB, bar, kc * 64, n * kT2N + (int)rank * (kT2N / 2), tap);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only; whole warp, one elected lane) =====================
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int q = pair; q < p.total_tiles; q += n_pairs) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kT2N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_ab + stage * kT2StageBytes;
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_k_sw128(sa);
+            const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(as));
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs drain their own TMEM half) =====================
+    const int q4 = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int row = q4 * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    const int ly = row / p.tw, lx = row - ly * p.tw;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t chunk_ctr = 0;
+    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
+    for (int q = pair; q < p.total_tiles; q += n_pairs) {
+      int n, tx, ty, b;
+      decode(q, n, tx, ty, b);
+      const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
+      const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * kT2N);
+      epilogue_nhwc_tile<kT2N, kT2Split, true, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+                                                      as ? tempty_l1 : tempty_l0, n, tx, ty, b, ox, oy, valid, row, lane,
+                                                      epi_tid, chunk_ctr, hsel, csum);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+    flush_colsum<kT2N, kT2Split>(p, csum, lane, hsel);
+    if (epi_tid < 32) {
+      if (elect_one()) tma_store_wait_read<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  conv_choose_tile(d->Wo, d->Ho, d->in_stride, d->y_pool != nullptr, &p.tw, &p.th);
+  p.pool = d->y_pool != nullptr ? 1 : 0;
+  p.store_full = (d->y != nullptr) ? 1 : 0;
+  p.tiles_x = (d->Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (d->Ho + p.th - 1) / p.th;
+  p.n_tiles = d->Cout_pad / kT2N;
+  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d->B;
+  const long long pairs = (m_tiles + 1) / 2;
+  DB_REQUIRE((m_tiles + 1) * p.n_tiles < (1ll << 24) && p.tiles_x < 65536 && p.tiles_y < 65536 && p.n_tiles < 65536,
+             "conv: too many tiles for one launch (%d x %d x %d x %d)", p.tiles_x, p.tiles_y, p.n_tiles, d->B);
+  p.total_tiles = (int)(pairs * p.n_tiles);
+  p.absmax = d->absmax;
+  p.gate = reinterpret_cast<const __half*>(d->gate);
+  p.out_scale = d->out_scale;
+  p.colsum = d->colsum;
+  p.mg_n = div_magic(p.n_tiles);
+  p.mg_x = div_magic(p.tiles_x);
+  p.mg_y = div_magic(p.tiles_y);
+  p.in_stride = d->in_stride;
+  p.taps = d->taps;
+  p.kchunks = d->Cin / 64;
+  memcpy(p.dy, d->tap_dy, sizeof(p.dy));
+  memcpy(p.dx, d->tap_dx, sizeof(p.dx));
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.residual_f32 = d->residual_f32;
+  p.y_f32 = d->y_f32;
+  p.Cout_pad = d->Cout_pad;
+  p.relu = d->relu;
+  p.cout_real = d->cout_real;
+
+  const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
+  const int budget = 232448 - 1024 - out_bytes - 256 - kT2N * 4;
+  int stages = budget / kT2StageBytes;
+  if (stages > 8) stages = 8;
+  DB_REQUIRE(stages >= 2, "conv_tc2: not enough shared memory for 2 stages");
+  p.stages = stages;
+  const int smem_bytes = 1024 + stages * kT2StageBytes + out_bytes + 256 + kT2N * 4;
+
+  CUtensorMap tmA, tmB, tmC, tmP;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmP, 0, sizeof(tmP));
+  const uint32_t es4[4] = {1, 1, 1, 1};
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+    const uint32_t s = (uint32_t)d->in_stride;
+    uint32_t box[4] = {64, (uint32_t)p.tw * s, (uint32_t)p.th * s, 1};
+    uint32_t es[4] = {1, s, s, 1};
+    DB_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv_tc2: TMA box too large (%u x %u)", box[1], box[2]);
+    if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es, "tc2 activation")) return -1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->taps};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {64, (uint32_t)(kT2N / 2), 1};
+    uint32_t es[3] = {1, 1, 1};
+    if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "tc2 weights")) return -1;
+  }
+  if (d->y_pool != nullptr) {
+    const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, Wp, Hp, (uint64_t)d->B};
+    uint64_t str[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw / 2, (uint32_t)p.th / 2, 1};
+    if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es4, "tc2 pooled output")) return -1;
+  }
+  if (d->y != nullptr) {
+    uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es4, "tc2 output")) return -1;
+  }
+  const bool plain = d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
+                     d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
+  auto kern = plain ? conv_tc2_kernel<true> : conv_tc2_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[plain]) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[plain] = true;
+  }
+  const int sms = device_sm_count() & ~1;
+  const int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
+  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Returns 1 and launches when the layer qualifies (and the kernel is switched on), 0 otherwise, <0 on error.
+int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DREAMB200_TC2");      // opt-in until validated on a GPU (tools/tc2_check.py)
+    on = e ? atoi(e) : 0;
+  }
+  if (!on) return 0;
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->Cout_pad % kT2N != 0) return 0;
+  if ((long long)d->B * d->Ho * d->Wo < 2 * 128) return 0;            // fewer than two M-tiles: nothing to pair
+  const int rc = launch_tc2(d, stream);
+  return rc == 0 ? 1 : rc;
+}
+
+}  // namespace db200
