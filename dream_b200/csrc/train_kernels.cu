@@ -1004,6 +1004,10 @@ static int wgrad_impl(const void* dy, const void* x, float* dw, int B, int H, in
   return launch_wgrad<64>(tmDY, tmX, p, stream);
 }
 
+namespace db200 {
+int try_wgrad3x3_pair(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
+                      cudaStream_t stream);   // wgrad_pair.cu (opt-in CTA-pair kernel)
+}
 extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad,
                                int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx, void* stream_v) {
   static int use_row_kernel = -1;
@@ -1021,7 +1025,11 @@ extern "C" int dreamb200_wgrad(const void* dy, const void* x, float* dw, int B, 
   }
   if (std3x3 && use_c64 && Cout_pad == 64)
     return wgrad3x3_c64_impl(dy, x, dw, B, H, W, Cin_pad, (cudaStream_t)stream_v);
-  if (std3x3) return wgrad3x3_impl(dy, x, dw, B, H, W, Cout_pad, Cin_pad, (cudaStream_t)stream_v);
+  if (std3x3) {
+    const int r = try_wgrad3x3_pair(dy, x, dw, B, H, W, Cout_pad, Cin_pad, (cudaStream_t)stream_v);   // opt-in
+    if (r != 0) return r > 0 ? 0 : r;
+    return wgrad3x3_impl(dy, x, dw, B, H, W, Cout_pad, Cin_pad, (cudaStream_t)stream_v);
+  }
   return wgrad_impl(dy, x, dw, B, H, W, H, W, H, W, 1, 1, 0, Cout_pad, Cin_pad, taps, tap_dy, tap_dx,
                     (cudaStream_t)stream_v);
 }
