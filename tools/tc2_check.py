@@ -79,7 +79,7 @@ def main():
             t0 = time.time()
             try:
                 p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name, outp], env=env,
-                                   capture_output=True, text=True, timeout=60)
+                                   capture_output=True, text=True, timeout=240)
                 line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
                 got[mode] = json.loads(line[-1][7:]) if line else {"error": (p.stderr[-600:] + p.stdout[-300:])}
             except subprocess.TimeoutExpired:
