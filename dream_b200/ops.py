@@ -110,7 +110,15 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
         if head_cout is not None:      # the head takes the slab kernel whenever it is a plain 3x3 over 64 padded channels
             rs = (T == 9 and stride == 1 and Cin == 64 and tuple(taps) == tuple(TAPS_3x3) and
                   os.environ.get("DREAMB200_RS_HEAD", "1") != "0")
-        tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % ("conv_rs" if rs else "conv_tc", block_n, T, Cin, Cout_pad, Ho, Wo, stride)
+        fam = "conv_rs" if rs else "conv_tc"
+        if rs and head_cout is None and Ho >= 32:      # mirror of try_conv_rs2 (conv_rs2.cu): the CTA-pair slab kernel
+            mode = int(os.environ.get("DREAMB200_RS2", "3"))
+            pair_util = Ho * Wo / (((Wo + 7) // 8) * ((Ho + 31) // 32) * 256.0)
+            want = (mode & 1) if (Cout_pad == 64 and Cin == 64) else (mode & 4) if Cout_pad == 64 else \
+                   ((mode & 8) if Cin == 64 else (mode & 2)) if Cout_pad == 128 else 0
+            if want and pair_util >= 0.8:
+                fam = "conv_rs2"
+        tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % (fam, block_n, T, Cin, Cout_pad, Ho, Wo, stride)
         PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
     else:
         check(lib().dreamb200_conv2d_fwd(C.byref(d), _stream()), "dreamb200_conv2d_fwd")
