@@ -56,6 +56,7 @@ _PROTOS = {
     "dreamb200_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "dreamb200_peaks_scratch_floats": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_longlong)]),
     "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
                         [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dreamb200_wgrad_deconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
@@ -79,7 +80,7 @@ _PROTOS = {
                              [C.c_void_p, C.c_void_p]),
 }
 
-# every symbol include/dreamb200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/dreamb200.h declares (checked by tests/test_host_logic.py::test_capi_exports_every_declared_symbol)
 DECLARED_SYMBOLS = tuple(_PROTOS.keys())
 
 

@@ -22,14 +22,10 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
 
+int device_sm_count();   // conv_tc.cu
+
 static int grid_for(long long work_items, int threads) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   long long blocks = (work_items + threads - 1) / threads;
   long long cap = (long long)sms * 16;
   if (blocks > cap) blocks = cap;

@@ -399,7 +399,7 @@ int device_sm_count() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (n <= 0) n = 148;   // query failed (no device yet): B200 default, re-queried never -- launches fail anyway
   }
   return n;
 }

@@ -278,12 +278,11 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
 
 // Returns 1 and launches when the layer qualifies (and the kernel is switched on), 0 otherwise, <0 on error.
 int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("DREAMB200_TC2");      // opt-in until validated on a GPU (tools/tc2_check.py)
-    on = e ? atoi(e) : 0;
-  }
-  if (!on) return 0;
+  // on by default since round 2 (bit-identical to conv_tc on every case of tools/tc2_check.py, 8-10 % faster per wide
+  // layer on a B200: profiles/r02_ab_pair_kernels.txt); DREAMB200_TC2=0 switches back for A/B runs.  Read per call so
+  // a test can flip it in-process.
+  const char* e = getenv("DREAMB200_TC2");
+  if (e && e[0] == '0') return 0;
   if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->Cout_pad % kT2N != 0) return 0;
   if ((long long)d->B * d->Ho * d->Wo < 2 * 128) return 0;            // fewer than two M-tiles: nothing to pair
   const int rc = launch_tc2(d, stream);

@@ -10,6 +10,7 @@
 #include "dreamb200.h"
 
 namespace db200 {
+int device_sm_count();
 
 struct NormParams {
   const uint8_t* x;
@@ -103,7 +104,7 @@ extern "C" int dreamb200_normalize_u8(const void* x_u8_nhwc, float* y_nchw, int 
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.stdv[c] = std3[c]; }
   const long long total = p.groups * B;
   long long blocks = (total + 255) / 256;
-  const long long cap = 148LL * 16;
+  const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   normalize_u8_kernel<<<(int)blocks, 256, 0, stream>>>(p);
   DB_CHECK_CUDA(cudaGetLastError());

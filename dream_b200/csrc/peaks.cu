@@ -11,13 +11,27 @@
 //      (image_proc.py:936-954), ordered (raster) compaction, 5x5 weighted centroid on the UNsmoothed
 //      map in fp64 with numpy's pairwise summation order (image_proc.py:961-998), plus the
 //      best / second-best scores needed by DreamNetwork.inference (network.py:548-577).
-// All three are HBM/L2 streaming kernels over 4*B*K*h*w bytes.
+// All three are HBM/L2 streaming kernels over 4*B*K*h*w bytes.  They remain as the path for maps too large for
+// shared memory (full-resolution decoders) or a Gaussian radius other than 12.
+//
+// peaks_fused_kernel (the default for sigma = 3 and maps up to ~160x160): ONE launch, one CTA per map.  The map is read
+// from HBM once into shared memory; both Gaussian passes, the peak test, the ordered compaction and the centroids run
+// there.  Same fp64 operations in the same order as the three-kernel path (bit-identical results), but every thread
+// filters a STRIP of 10 consecutive outputs from a register window of 34 inputs, so each input is read from shared
+// memory and converted to fp64 once per 10 outputs instead of once per tap (the three-kernel path was bound by a
+// 25-long dependent chain with two global loads and two fp32->fp64 conversions per tap).  The intermediate and the
+// smoothed map are stored transposed with an odd pitch so that both passes and the peak test are bank-conflict free.
+// What bounds it: the fp64 pipe (2 * 37 fp64 operations per pixel), not HBM -- see DESIGN.md 3.4.
 //
 // dreamb200_softargmax: SoftArgmaxPavlo.forward (dream/spatial_softmax.py:24-95), one CTA per map.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dreamb200.h"
 
 namespace db200 {
+
+int device_sm_count();
 
 constexpr int kMaxRadius = 32;
 struct GaussW {
@@ -199,6 +213,225 @@ collect_peaks_kernel(const float* __restrict__ ori, const float* __restrict__ sm
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused path: one CTA per map, everything in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedRadius = 12;
+constexpr int kStrip = 10;
+constexpr int kFusedThreads = 256;
+constexpr int kMaxMaskWords = 1024;          // h*w <= 32768 pixels
+
+// One separable pass over a [n_other lines] x [n_axis samples] map.  Element (line o, sample i) of the source is
+// src[o*s_other + i*s_axis]; thread tasks are (strip, line) with the line index fastest, so that consecutive lanes
+// touch consecutive lines (the caller picks layouts where that is conflict free).  Arithmetic = gauss_pass_kernel's.
+__device__ __forceinline__ void gauss_strips(const float* __restrict__ src, int s_axis, int s_other,
+                                             float* __restrict__ dst, int d_axis, int d_other, int n_axis,
+                                             int n_other, const GaussW& gw) {
+  const int strips = (n_axis + kStrip - 1) / kStrip;
+  const int tasks = strips * n_other;
+  for (int t = threadIdx.x; t < tasks; t += kFusedThreads) {
+    const int strip = t / n_other;
+    const int o = t - strip * n_other;
+    const int c0 = strip * kStrip;
+    const float* line = src + o * s_other;
+    double v[kStrip + 2 * kFusedRadius];
+    if (c0 >= kFusedRadius && c0 + kStrip + kFusedRadius <= n_axis) {
+#pragma unroll
+      for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) v[j] = (double)line[(c0 - kFusedRadius + j) * s_axis];
+    } else {
+#pragma unroll
+      for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) {
+        int i = c0 - kFusedRadius + j;
+        if (i < 0 || i >= n_axis) i = reflect_idx(i, n_axis);
+        v[j] = (double)line[i * s_axis];
+      }
+    }
+    float* out = dst + o * d_other + c0 * d_axis;
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) {
+      double acc = __dmul_rn(v[j + kFusedRadius], gw.w[0]);
+#pragma unroll
+      for (int d = kFusedRadius; d >= 1; --d)
+        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[j + kFusedRadius - d], v[j + kFusedRadius + d]), gw.w[d]));
+      if (c0 + j < n_axis) out[j * d_axis] = __double2float_rn(acc);
+    }
+  }
+}
+
+// 5x5 weighted centroid around (px, py) on the unsmoothed map (image_proc.py:961-998); out of line: peaks are rare and
+// its 75 fp64 temporaries must not squeeze the register budget of the filter loops.
+static __device__ __noinline__ void peak_centroid(const float* __restrict__ mo, int h, int w, int px, int py,
+                                                  double offset, double* cx_out, double* cy_out) {
+  double wts[25], xv[25], yv[25];
+#pragma unroll
+  for (int k = 0; k < 25; ++k) { wts[k] = 0.0; xv[k] = 0.0; yv[k] = 0.0; }
+#pragma unroll
+  for (int i = -2; i <= 2; ++i) {       // row offset
+#pragma unroll
+    for (int j = -2; j <= 2; ++j) {     // column offset
+      const int yy = py + i, xx = px + j;
+      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+      const int k = (j + 2) * 5 + (i + 2);
+      wts[k] = (double)__ldg(mo + yy * w + xx);
+      xv[k] = (double)xx;
+      yv[k] = (double)yy;
+    }
+  }
+  const double scl = pairwise25(wts);
+  double cx, cy;
+  if (scl == 0.0) {
+    cx = (double)px + offset;
+    cy = (double)py + offset;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { xv[k] = __dmul_rn(xv[k], wts[k]); yv[k] = __dmul_rn(yv[k], wts[k]); }
+    cx = __dadd_rn(__ddiv_rn(pairwise25(xv), scl), offset);
+    cy = __dadd_rn(__ddiv_rn(pairwise25(yv), scl), offset);
+  }
+  *cx_out = cx;
+  *cy_out = cy;
+}
+
+// combined best / runner-up of two candidate sets (commutative: multiset semantics, ties -> earliest raster index)
+__device__ __forceinline__ void top2_merge(Top2& t, const Top2& o) {
+  if (o.n == 0) return;
+  const float o_s1 = o.s1;
+  const int o_n = o.n;
+  top2_insert(t, o.s0, o.i0, o.x0, o.y0);
+  if (o_n >= 2 && (t.n == 1 || o_s1 > t.s1)) { t.s1 = o_s1; t.n = 2; }
+}
+
+__device__ __forceinline__ Top2 top2_shfl_xor(const Top2& t, int m) {
+  Top2 o;
+  o.s0 = __shfl_xor_sync(0xffffffffu, t.s0, m);
+  o.s1 = __shfl_xor_sync(0xffffffffu, t.s1, m);
+  o.i0 = __shfl_xor_sync(0xffffffffu, t.i0, m);
+  o.n = __shfl_xor_sync(0xffffffffu, t.n, m);
+  o.x0 = __shfl_xor_sync(0xffffffffu, t.x0, m);
+  o.y0 = __shfl_xor_sync(0xffffffffu, t.y0, m);
+  return o;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2)
+peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, const __grid_constant__ GaussW gw,
+                   double offset, int cap, double* __restrict__ peak_xy, float* __restrict__ peak_score,
+                   int32_t* __restrict__ peak_ij, int32_t* __restrict__ counts, double* __restrict__ summary) {
+  extern __shared__ __align__(16) float fsm[];
+  const int hp = h | 1;                        // odd pitch of the transposed buffers
+  const int total = h * w;
+  float* bufA = fsm;                           // the map, row major [h][w]; later the smoothed map, transposed [w][hp]
+  float* bufB = fsm + w * hp;                  // axis-0 result, transposed [w][hp]
+  __shared__ uint32_t mask[kMaxMaskWords];
+  __shared__ int pref[kMaxMaskWords];
+  __shared__ Top2 warp_top[kFusedThreads / 32];
+  __shared__ int total_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int words = (total + 31) >> 5;
+
+  for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
+    const float* mo = maps + (long long)map * total;
+    // ---- HBM -> shared, once
+    if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(mo) & 15) == 0) {
+      const float4* m4 = reinterpret_cast<const float4*>(mo);
+      float4* a4 = reinterpret_cast<float4*>(bufA);
+      for (int i = tid; i < (total >> 2); i += kFusedThreads) a4[i] = __ldg(m4 + i);
+    } else {
+      for (int i = tid; i < total; i += kFusedThreads) bufA[i] = __ldg(mo + i);
+    }
+    __syncthreads();
+    // ---- axis 0 (along y): lines = columns x; reads bufA[y*w + x], writes bufB[x*hp + y]
+    gauss_strips(bufA, w, 1, bufB, 1, hp, h, w, gw);
+    __syncthreads();
+    // ---- axis 1 (along x): lines = rows y; reads bufB[x*hp + y], writes bufA[x*hp + y]
+    gauss_strips(bufB, hp, 1, bufA, hp, 1, w, h, gw);
+    __syncthreads();
+    // ---- peak test -> bitmask in raster order
+    const float* sm = bufA;
+    for (int base = wid * 32; base < words * 32; base += kFusedThreads) {
+      const int idx = base + lane;
+      bool is_peak = false;
+      if (idx < total) {
+        const int py = idx / w, px = idx - py * w;
+        const float* c = sm + px * hp + py;
+        const float v = c[0];
+        const float up = py > 0 ? c[-1] : 0.0f;
+        const float dn = py < h - 1 ? c[1] : 0.0f;
+        const float lf = px > 0 ? c[-hp] : 0.0f;
+        const float rt = px < w - 1 ? c[hp] : 0.0f;
+        is_peak = (v >= up) && (v >= dn) && (v >= lf) && (v >= rt) && (v > 0.01f);
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, is_peak);
+      if (lane == 0) mask[base >> 5] = ballot;
+    }
+    __syncthreads();
+    // ---- exclusive prefix of the per-word counts (one warp)
+    if (wid == 0) {
+      int running = 0;
+      for (int b = 0; b < words; b += 32) {
+        const int c = b + lane < words ? __popc(mask[b + lane]) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += n;
+        }
+        if (b + lane < words) pref[b + lane] = running + inc - c;
+        running += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) total_s = running;
+    }
+    __syncthreads();
+    // ---- centroids of the peaks (few per map): one thread per mask word
+    Top2 mine;
+    mine.n = 0; mine.i0 = -1; mine.s0 = 0.f; mine.s1 = 0.f; mine.x0 = 0.0; mine.y0 = 0.0;
+    for (int wd = tid; wd < words; wd += kFusedThreads) {
+      uint32_t bits = mask[wd];
+      int slot = pref[wd];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int idx = wd * 32 + b;
+        const int py = idx / w, px = idx - py * w;
+        double cx, cy;
+        peak_centroid(mo, h, w, px, py, offset, &cx, &cy);
+        const float score = __ldg(mo + idx);
+        if (slot < cap) {
+          const size_t o = (size_t)map * cap + slot;
+          peak_xy[2 * o] = cx;
+          peak_xy[2 * o + 1] = cy;
+          peak_score[o] = score;
+          peak_ij[2 * o] = px;
+          peak_ij[2 * o + 1] = py;
+        }
+        ++slot;
+        top2_insert(mine, score, idx, cx, cy);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const Top2 o = top2_shfl_xor(mine, m);
+      top2_merge(mine, o);
+    }
+    if (lane == 0) warp_top[wid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+      Top2 t = warp_top[0];
+      for (int i = 1; i < kFusedThreads / 32; ++i) top2_merge(t, warp_top[i]);
+      counts[map] = total_s;
+      summary[4 * map + 0] = t.x0;
+      summary[4 * map + 1] = t.y0;
+      summary[4 * map + 2] = (double)t.s0;
+      summary[4 * map + 3] = (double)t.s1;
+    }
+    __syncthreads();                           // bufA / mask / warp_top are reused by the next map
+  }
+}
+
+static size_t fused_smem_bytes(int h, int w) { return (size_t)2 * w * (h | 1) * sizeof(float); }
+static bool fused_ok(int h, int w, int radius) {
+  return radius == kFusedRadius && (long long)h * w <= 32LL * kMaxMaskWords && fused_smem_bytes(h, w) <= 200 * 1024;
+}
+
+// ---------------------------------------------------------------------------------------------
 // SoftArgmaxPavlo: 7x7 average pool (zero padded, /49) -> max -> exp(beta*(v-max)) -> expected x,y
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float block_reduce_max(float v, float* sh) {
@@ -273,7 +506,7 @@ extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, cons
                                double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
                                int32_t* peak_ij, int32_t* counts, double* summary, void* stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
-  DB_REQUIRE(maps && gauss_w && scratch && peak_xy && peak_score && peak_ij && counts && summary,
+  DB_REQUIRE(maps && gauss_w && peak_xy && peak_score && peak_ij && counts && summary,
              "peaks: null pointer");
   DB_REQUIRE(n_maps > 0 && h > 0 && w > 0, "peaks: empty input (n_maps=%d h=%d w=%d)", n_maps, h, w);
   DB_REQUIRE(radius >= 0 && radius <= kMaxRadius, "peaks: radius %d out of range", radius);
@@ -281,17 +514,37 @@ extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, cons
   DB_REQUIRE((long long)h * w < (1ll << 30), "peaks: map too large");
   GaussW gw;
   for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
+  if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) {
+    const size_t smem = fused_smem_bytes(h, w);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      DB_CHECK_CUDA(cudaFuncSetAttribute(peaks_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    peaks_fused_kernel<<<n_maps, kFusedThreads, smem, stream>>>(maps, n_maps, h, w, gw, offset, cap, peak_xy,
+                                                                 peak_score, peak_ij, counts, summary);
+    DB_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
+  DB_REQUIRE(scratch, "peaks: this map size / radius takes the three-kernel path and needs the scratch buffer");
   const long long total = (long long)n_maps * h * w;
   float* tmp = scratch;
   float* smooth = scratch + total;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > (long long)device_sm_count() * 32) blocks = (long long)device_sm_count() * 32;
   gauss_pass_kernel<0><<<(int)blocks, 256, 0, stream>>>(maps, tmp, n_maps, h, w, gw, radius);
   gauss_pass_kernel<1><<<(int)blocks, 256, 0, stream>>>(tmp, smooth, n_maps, h, w, gw, radius);
   collect_peaks_kernel<<<n_maps, kPeakThreads, 0, stream>>>(maps, smooth, h, w, offset, cap, peak_xy, peak_score,
                                                           peak_ij, counts, summary);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
+  return 0;
+}
+
+extern "C" int dreamb200_peaks_scratch_floats(int n_maps, int h, int w, int radius, long long* n_floats) {
+  DB_REQUIRE(n_floats, "peaks_scratch_floats: null pointer");
+  *n_floats = (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) ? 0 : 2LL * n_maps * h * w;
   return 0;
 }
 

@@ -1063,7 +1063,7 @@ extern "C" int dreamb200_scale_mask_bias_f16(void* dy, const void* y, const floa
                                              int C, void* stream) {
   DB_REQUIRE(dy && db && rows > 0 && C % 64 == 0, "scale_mask_bias: bad arguments");
   long long bx = (rows + 8 * 16 - 1) / (8 * 16);
-  if (bx > 148 * 8) bx = 148 * 8;
+  if (bx > device_sm_count() * 8) bx = device_sm_count() * 8;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)(C / 64));
   scale_mask_bias_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__half*>(dy),
@@ -1129,7 +1129,7 @@ extern "C" int dreamb200_upsample2_bwd_nhwc(const void* dy, void* dx, int B, int
 extern "C" int dreamb200_bias_grad(const void* dy, float* db, long long rows, int C, void* stream) {
   DB_REQUIRE(dy && db && rows > 0 && C % 64 == 0, "bias_grad: bad arguments");
   long long bx = (rows + 8 * 64 - 1) / (8 * 64);
-  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx > device_sm_count() * 4) bx = device_sm_count() * 4;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)(C / 64));
   bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(dy), db, rows, C);
@@ -1140,7 +1140,7 @@ extern "C" int dreamb200_bias_grad(const void* dy, float* db, long long rows, in
 
 static dim3 reduce_grid(long long rows, int C) {
   long long bx = (rows + 8 * 64 - 1) / (8 * 64);
-  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx > device_sm_count() * 4) bx = device_sm_count() * 4;
   if (bx < 1) bx = 1;
   return dim3((unsigned)bx, (unsigned)(C / 64));
 }

@@ -174,12 +174,10 @@ wgrad3x3_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 // Returns 1 and launches when the layer qualifies (and the kernel is switched on), 0 otherwise, <0 on error.
 int try_wgrad3x3_pair(const void* dy, const void* x, float* dw, int B, int H, int W, int Cout_pad, int Cin_pad,
                       cudaStream_t stream) {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("DREAMB200_WGRAD3_2SM");   // opt-in until validated on a GPU (tools/wgrad_pair_check.py)
-    on = e ? atoi(e) : 0;
-  }
-  if (!on || Cout_pad % 256 != 0 || Cin_pad % 128 != 0) return 0;
+  // on by default since round 2 (tools/wgrad_pair_check.py green on a B200, 7-14 % faster on the 256 / 512-channel
+  // layers: profiles/r02_ab_pair_kernels.txt); DREAMB200_WGRAD3_2SM=0 switches back.  Read per call.
+  const char* e = getenv("DREAMB200_WGRAD3_2SM");
+  if ((e && e[0] == '0') || Cout_pad % 256 != 0 || Cin_pad % 128 != 0) return 0;
   WgradPairParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;

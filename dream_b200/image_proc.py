@@ -49,11 +49,13 @@ def find_peaks_device(maps, offset_due_to_upsampling, cap=64):
     n_maps = maps.numel() // (h * w)
     wts, radius = gaussian_half_kernel()
     table = PeakTable(n_maps, cap, maps.device)
-    scratch = torch.empty((2, n_maps, h, w), dtype=torch.float32, device=maps.device)
+    need = C.c_longlong(0)
+    check(lib().dreamb200_peaks_scratch_floats(n_maps, h, w, radius, C.byref(need)), "dreamb200_peaks_scratch_floats")
+    scratch = torch.empty((need.value,), dtype=torch.float32, device=maps.device) if need.value else None
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     check(lib().dreamb200_peaks(C.c_void_p(maps.data_ptr()), n_maps, h, w,
                                 wts.ctypes.data_as(C.c_void_p), radius, float(offset_due_to_upsampling),
-                                C.c_void_p(scratch.data_ptr()), cap, C.c_void_p(table.xy.data_ptr()),
+                                C.c_void_p(scratch.data_ptr() if scratch is not None else 0), cap, C.c_void_p(table.xy.data_ptr()),
                                 C.c_void_p(table.score.data_ptr()), C.c_void_p(table.ij.data_ptr()),
                                 C.c_void_p(table.counts.data_ptr()), C.c_void_p(table.summary.data_ptr()),
                                 stream), "dreamb200_peaks")

@@ -111,6 +111,9 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
             rs = (T == 9 and stride == 1 and Cin == 64 and tuple(taps) == tuple(TAPS_3x3) and
                   os.environ.get("DREAMB200_RS_HEAD", "1") != "0")
         fam = "conv_rs" if rs else "conv_tc"
+        if (not rs and head_cout is None and Cout_pad % 256 == 0 and B * Ho * Wo >= 256 and
+                os.environ.get("DREAMB200_TC2", "1")[:1] != "0"):      # mirror of try_conv_tc2 (conv_tc2.cu)
+            fam = "conv_tc2"
         if rs and head_cout is None and Ho >= 32:      # mirror of try_conv_rs2 (conv_rs2.cu): the CTA-pair slab kernel
             mode = int(os.environ.get("DREAMB200_RS2", "3"))
             pair_util = Ho * Wo / (((Wo + 7) // 8) * ((Ho + 31) // 32) * 256.0)

@@ -119,12 +119,14 @@ int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int H, int W,
 
 /* peaks_from_belief_maps for n_maps = B*K maps of h x w fp32 (contiguous).
    gauss_w: 13 fp64 taps w[0..12] for |offset| 0..12 (host computes them like scipy).
-   scratch: 2*n_maps*h*w floats.  peak table: capacity `cap` per map, rows
+   scratch: dreamb200_peaks_scratch_floats() floats -- 0 (pass NULL) when the map fits the fused one-launch kernel
+   (radius 12 and 2*w*(h|1)*4 bytes of shared memory <= 200 KB), else 2*n_maps*h*w.  peak table: capacity `cap` per map, rows
    (x:f64, y:f64, score:f32, pad) ; counts[n_maps] = true count (may exceed cap).
    summary[n_maps*4] doubles: best x, best y, best score, second score. */
 int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
                     double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
+int dreamb200_peaks_scratch_floats(int n_maps, int h, int w, int radius, long long* n_floats);
 
 /* ---- backward (training) ------------------------------------------------------------------ */
 /* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy, x NHWC fp16 [B,H,W,Cout_pad|Cin_pad],

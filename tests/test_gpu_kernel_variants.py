@@ -1,0 +1,187 @@
+"""GPU tests (-m gpu) of the kernels that have a second implementation of the same op: each default kernel must agree
+with its fallback through the C-ABI -- bit for bit where the arithmetic order is the same (fused vs three-kernel peak
+extraction, conv_tc2 vs conv_tc), to fp32 atomic-order noise where it is not (wgrad3x3_pair vs wgrad3x3) -- and with
+the oracle.  The switches are environment variables the library reads on every call."""
+import os
+from contextlib import contextmanager
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_peaks  # noqa: E402  (checker only)
+
+
+@contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    try:
+        for k, v in kw.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _table_np(t):
+    return {k: getattr(t, k).cpu().numpy() for k in ("xy", "score", "ij", "counts", "summary")}
+
+
+def _maps(rng, n, h, w, kind):
+    if kind == "blobs":
+        m = np.zeros((n, h, w), np.float32)
+        yy, xx = np.mgrid[0:h, 0:w]
+        for i in range(n):
+            for _ in range(int(rng.integers(0, 5))):
+                cx, cy, a = rng.uniform(-2, w + 2), rng.uniform(-2, h + 2), rng.uniform(0.05, 1.0)
+                m[i] += (a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 8.0)).astype(np.float32)
+            m[i] += rng.standard_normal((h, w)).astype(np.float32) * 0.01
+        return m
+    if kind == "noise":                     # many local maxima above the threshold: exercises the ordered compaction
+        return (rng.standard_normal((n, h, w)) * 0.5 + 0.3).astype(np.float32)
+    if kind == "plateau":                   # every pixel passes the >= test: counts far above the table capacity
+        m = np.full((n, h, w), 0.5, np.float32)
+        m[1::2] = 0.0                       # ... and all-zero maps: no peak at all
+        return m
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("h,w,kind", [(100, 100, "blobs"), (100, 100, "noise"), (37, 53, "blobs"), (5, 7, "noise"),
+                                      (1, 9, "noise"), (120, 160, "blobs"), (64, 48, "plateau"), (13, 11, "plateau")])
+def test_fused_peaks_equal_three_kernel_path_and_oracle(h, w, kind, built_lib):
+    from dream_b200 import image_proc
+    rng = np.random.default_rng(h * 1000 + w)
+    n = 21
+    maps = _maps(rng, n, h, w, kind)
+    dev = torch.from_numpy(maps).cuda()
+    with env(DREAMB200_PEAKS_UNFUSED=None):
+        fused = _table_np(image_proc.find_peaks_device(dev, 0.4395, cap=32))
+    with env(DREAMB200_PEAKS_UNFUSED="1"):
+        three = _table_np(image_proc.find_peaks_device(dev, 0.4395, cap=32))
+    assert np.array_equal(fused["counts"], three["counts"])
+    for i in range(n):
+        c = min(int(fused["counts"][i]), 32)
+        for k in ("xy", "score", "ij"):
+            assert np.array_equal(fused[k][i, :c], three[k][i, :c]), (i, k)
+        if fused["counts"][i] > 0:
+            assert np.array_equal(fused["summary"][i], three["summary"][i]), i
+    # ... and the integer peak set equals scipy's (oracle) on every map
+    for i in range(n):
+        sm = ref_peaks.gaussian_filter_f32(maps[i])
+        ys, xs = np.nonzero(ref_peaks.peak_mask(sm))
+        assert fused["counts"][i] == len(xs), i
+        c = min(len(xs), 32)
+        assert np.array_equal(fused["ij"][i, :c, 0], xs[:c]) and np.array_equal(fused["ij"][i, :c, 1], ys[:c]), i
+
+
+def test_fused_peaks_full_batch_shape_matches_oracle_decisions(built_lib):
+    """B=128 x 7 maps of 100x100 (the benchmarked shape) through the fused kernel: counts, refined coordinates and the
+    keypoint decision equal the oracle's on a sample of the maps, and the two device paths agree on all of them."""
+    from dream_b200 import image_proc
+    rng = np.random.default_rng(5)
+    maps = _maps(rng, 896, 100, 100, "blobs")
+    dev = torch.from_numpy(maps).cuda()
+    t = image_proc.find_peaks_device(dev, 0.4395)
+    sel = image_proc.select_keypoints_device(t, 0.25).cpu().numpy()
+    with env(DREAMB200_PEAKS_UNFUSED="1"):
+        t3 = image_proc.find_peaks_device(dev, 0.4395)
+        sel3 = image_proc.select_keypoints_device(t3, 0.25).cpu().numpy()
+    assert np.array_equal(sel, sel3) and torch.equal(t.counts, t3.counts)
+    idx = rng.choice(896, 48, replace=False)
+    ref = ref_peaks.peaks_from_belief_maps(maps[idx], 0.4395)
+    ref_sel = np.array(ref_peaks.select_keypoints(ref))
+    assert np.array_equal(sel[idx], ref_sel)
+    xy = t.xy.cpu().numpy()
+    for j, i in enumerate(idx):
+        assert int(t.counts[i]) == len(ref[j])
+        for s, p in enumerate(ref[j][:64]):
+            assert xy[i, s, 0] == p[0] and xy[i, s, 1] == p[1]
+
+
+CONV_CASES = {   # name: (B, H, W, Cin, Cout, kind)
+    "256_256_50": (2, 50, 50, 256, 256, "3x3"),
+    "128_256_100_pool": (2, 100, 100, 128, 256, "pool"),
+    "256_512_26x30_s2": (2, 26, 30, 256, 512, "s2"),
+    "256_1024_25_1x1res": (2, 25, 25, 256, 1024, "1x1res"),
+    "512_512_25_odd_tiles": (1, 25, 25, 512, 512, "3x3"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONV_CASES))
+def test_conv_pair_kernel_is_bit_identical_to_single_cta(name, built_lib):
+    from dream_b200 import ops
+    B, H, W, Cin, Cout, kind = CONV_CASES[name]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.randn((B, H, W, Cin), device="cuda", generator=g) * 0.5).half()
+    ksz = 1 if kind == "1x1res" else 3
+    stride = 2 if kind == "s2" else 1
+    pad = ksz // 2
+    w = torch.randn((Cout, Cin, ksz, ksz), device="cuda", generator=g) * (1.0 / (Cin * ksz * ksz) ** 0.5)
+    bias = torch.randn((Cout,), device="cuda", generator=g) * 0.1
+    rs = [(r, s) for r in range(ksz) for s in range(ksz)]
+    taps = [(r - pad, s - pad) for r, s in rs]
+    Ho, Wo = (H + 2 * pad - ksz) // stride + 1, (W + 2 * pad - ksz) // stride + 1
+    wp, bp = ops.pack_conv_weight(w, rs), ops.pad_bias(bias, Cout, "cuda")
+    res32 = torch.randn((B, Ho, Wo, Cout), device="cuda", generator=g) if kind == "1x1res" else None
+
+    def run():
+        kw = {"relu": True, "stride": stride}
+        if kind == "pool":
+            kw["pool"] = "both"
+        if kind == "1x1res":
+            kw["residual_f32"] = res32
+            kw["y_f32"] = torch.empty((B, Ho, Wo, Cout), device="cuda")
+        y = ops.conv_taps(x, wp, bp, taps, Ho, Wo, **kw)
+        outs = [t for t in (y if isinstance(y, tuple) else (y,)) if t is not None]
+        if kind == "1x1res":
+            outs.append(kw["y_f32"])
+        torch.cuda.synchronize()
+        return outs
+
+    with env(DREAMB200_TC2="0"):
+        single = run()
+    with env(DREAMB200_TC2="1"):
+        pair = run()
+    assert len(single) == len(pair)
+    for a, b in zip(single, pair):
+        assert torch.equal(a, b)
+    # ... and both are the convolution (fp32 torch reference of the same fp16 operands)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), bias, stride=stride, padding=pad)
+    if res32 is not None:
+        ref = ref + res32.permute(0, 3, 1, 2)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    got = pair[-1] if kind == "1x1res" else pair[0]
+    assert (got.float() - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(3, 25, 25, 128, 256), (2, 50, 37, 256, 256), (2, 13, 13, 512, 512),
+                                         (2, 1, 9, 256, 512)])
+def test_wgrad_pair_kernel_matches_single_cta_and_autograd(B, H, W, Ci, Co, built_lib):
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn((B, H, W, Ci), device="cuda", generator=g) * 0.5).half()
+    dy = (torch.randn((B, H, W, Co), device="cuda", generator=g) * 0.5).half()
+    with env(DREAMB200_WGRAD3_2SM="0"):
+        single = ops.wgrad(dy, x, ops.TAPS_3x3)
+    with env(DREAMB200_WGRAD3_2SM="1"):
+        pair = ops.wgrad(dy, x, ops.TAPS_3x3)
+    torch.cuda.synchronize()
+    scale = single.abs().max().item()
+    assert (single - pair).abs().max().item() <= 1e-5 * scale          # same products, different fp32 summation order
+    xr = x.permute(0, 3, 1, 2).float()
+    wz = torch.zeros((Co, Ci, 3, 3), device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.nn.functional.conv2d(xr, wz, padding=1).backward(dy.permute(0, 3, 1, 2).float())
+    ref = wz.grad.permute(2, 3, 0, 1).reshape(9, Co, Ci)
+    assert (pair - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()

@@ -38,4 +38,10 @@ elif target == "wgrad256":
     dy = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
     for _ in range(3):
         ops.wgrad(dy, x, ops.TAPS_3x3)
+elif target == "peaks":            # peak extraction on B*7 belief maps of 100x100 (peaks_fused_kernel)
+    from dream_b200 import image_proc
+    maps = torch.randn((B * 7, 100, 100), device="cuda", generator=g) * 0.2
+    maps[:, 40:44, 60:64] += 1.0
+    for _ in range(3):
+        image_proc.find_peaks_device(maps, 0.4395)
 torch.cuda.synchronize()

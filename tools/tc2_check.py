@@ -1,6 +1,6 @@
-"""Bring-up harness for the CTA-pair wide-layer kernel (conv_tc2.cu, opt-in DREAMB200_TC2=1): every (case, mode) runs
+"""Bring-up harness for the CTA-pair wide-layer kernel (conv_tc2.cu; default since round 2, DREAMB200_TC2=0 switches it off): every (case, mode) runs
 in its own subprocess (a trapped kernel kills only that run); outputs are compared bit for bit with conv_tc and the
-big cases are timed.  python tools/tc2_check.py [case ...]      (NOT yet run on a GPU: written after round 1's budget)"""
+big cases are timed.  python tools/tc2_check.py [case ...]      (round 2: ALL IDENTICAL on a B200, profiles/r02_ab_pair_kernels.txt)"""
 import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

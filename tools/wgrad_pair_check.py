@@ -1,6 +1,6 @@
-"""Bring-up harness for the CTA-pair weight-gradient kernel (wgrad_pair.cu, opt-in DREAMB200_WGRAD3_2SM=1): every
+"""Bring-up harness for the CTA-pair weight-gradient kernel (wgrad_pair.cu; default since round 2, DREAMB200_WGRAD3_2SM=0 switches it off): every
 (case, mode) in its own subprocess; dW is compared with the single-CTA kernel (fp32 atomics: not bit-exact, gate 1e-5
-of the largest entry) and with torch autograd, and timed.   (NOT yet run on a GPU: written after round 1's budget)"""
+of the largest entry) and with torch autograd, and timed.   (round 2: ALL OK on a B200, profiles/r02_ab_pair_kernels.txt)"""
 import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
