@@ -57,6 +57,8 @@ _PROTOS = {
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "dreamb200_peaks_scratch_floats": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_longlong)]),
+    "dreamb200_gaussian_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +
                         [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dreamb200_wgrad_deconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +

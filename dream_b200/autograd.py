@@ -143,6 +143,16 @@ class _HourglassTrainFn(torch.autograd.Function):
         model, tape = ctx.model, ctx.tape
         P = model.plan()
         grads = {}
+        # multi-GPU training: finished parameter gradients go straight into the GradReducer's flat bucket buffer
+        # (dream_b200.distributed), whose all-reduce starts while the layers below are still being differentiated
+        sink = getattr(model, "_grad_sink", None)
+
+        def emit(name, param, value):
+            if sink is not None and sink.accepts(param):
+                sink.deposit(param, value)
+            else:
+                grads[name] = value.contiguous()
+
         go = grad_out.contiguous().float()
         # fp16 gradients: every layer's dY is re-scaled by a power of two (computed on the device, no host
         # sync) so that max|dY| stays near 2^8; `cum` is the product of all factors applied so far and the
@@ -211,13 +221,13 @@ class _HourglassTrainFn(torch.autograd.Function):
                     f, inv = ops.loss_scale_step(amax, cum)
                     db = ops.scale_mask_bias_(g, yout if pc.relu else None, f)
                 if node.bias is not None:
-                    grads[key + ".bias"] = db[:cout] * inv
+                    emit(key + ".bias", node.bias, db[:cout] * inv)
                 if kind == "first":
                     if xin.dtype == torch.float32:                                     # the raw input (fused path)
                         dw = ops.wgrad_first(g, xin)[:cout]                            # [co, (r,s,c)]
                     else:                                                              # the im2col'ed input
                         dw = ops.wgrad(g, xin, [(0, 0)])[0, :cout, :27]
-                    grads[key + ".weight"] = (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+                    emit(key + ".weight", node.weight, (dw * inv).view(cout, 3, 3, 3).permute(0, 3, 1, 2))
                     if DEBUG_CAPTURE is not None:
                         DEBUG_CAPTURE.append((key, None, cum.clone(), xin, None, None, None))
                     g = None                                                           # the image needs no grad
@@ -248,7 +258,7 @@ class _HourglassTrainFn(torch.autograd.Function):
                 if deconv:
                     # y[2p + (ky-1, kx-1)] += x[p] W[:, :, ky, kx]  =>  dW[tap] = sum_p dY[2p + tap-1] (x) X[p]
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3, deconv=True)[:, :cout, :cin]      # [9, co, ci]
-                    grads[key + ".weight"] = (dw * inv_here).permute(2, 1, 0).reshape(cin, cout, 3, 3).contiguous()
+                    emit(key + ".weight", node.weight, (dw * inv_here).permute(2, 1, 0).reshape(cin, cout, 3, 3))
                     # dX[p] = sum_taps W[:, :, tap] dY[2p + tap-1]: a stride-2 3x3 conv over dY
                     rs = [(r, s_) for r in range(3) for s_ in range(3)]
                     wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=xin.shape[3])
@@ -256,7 +266,7 @@ class _HourglassTrainFn(torch.autograd.Function):
                                       gate=gate_t, out_scale=f_out, colsum=db_ready)
                 else:
                     dw = ops.wgrad(g, xin, ops.TAPS_3x3)[:, :cout, :cin]               # [9, co, ci]
-                    grads[key + ".weight"] = (dw * inv_here).permute(1, 2, 0).reshape(cout, cin, 3, 3).contiguous()
+                    emit(key + ".weight", node.weight, (dw * inv_here).permute(1, 2, 0).reshape(cout, cin, 3, 3))
                     wd, taps = _dgrad_pack(node.weight, xin.shape[3], g.shape[3])
                     g = ops.conv_taps(g, wd, None, taps, H, W, absmax=amax,
                                       gate=gate_t, out_scale=f_out, colsum=db_ready)

@@ -140,6 +140,14 @@ class _ResnetTrainFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         model, tape = ctx.model, ctx.tape
         grads = {}
+        sink = getattr(model, "_grad_sink", None)                # multi-GPU: dream_b200.distributed.GradReducer
+
+        def emit(name, param, value):
+            if sink is not None and sink.accepts(param):
+                sink.deposit(param, value)                       # its bucket's all-reduce may start right here
+            else:
+                grads[name] = value.contiguous()
+
         G = {}                                                   # id(tensor) -> accumulated fp16 gradient
 
         def acc(t, g):
@@ -156,9 +164,9 @@ class _ResnetTrainFn(torch.autograd.Function):
         hn = models._node_for(model, ctx.head)
         K, cin = hn.weight.shape[0], hn.weight.shape[1]
         inv = 1.0 / cum
-        grads[ctx.head + ".bias"] = ops.bias_grad(g)[:K] * inv
+        emit(ctx.head + ".bias", hn.bias, ops.bias_grad(g)[:K] * inv)
         dw = ops.wgrad(g, ctx.head_in, [(0, 0)])[0, :K, :cin]
-        grads[ctx.head + ".weight"] = (dw * inv).reshape(K, cin, 1, 1).contiguous()
+        emit(ctx.head + ".weight", hn.weight, (dw * inv).reshape(K, cin, 1, 1))
         wd = ops.pack_conv_weight(hn.weight.detach().permute(1, 0, 2, 3), [(0, 0)], cin_pad=64,
                                   cout_pad=ctx.head_in.shape[3])
         B, H, W, _ = ctx.head_in.shape
@@ -193,8 +201,8 @@ class _ResnetTrainFn(torch.autograd.Function):
             sum_dy, sum_dyz = ops.bn_bwd_reduce(g, u.z)
             gamma = _pad_vec(bn.weight, Cp)
             dgamma = u.invstd * (sum_dyz - u.mean * sum_dy)
-            grads[u.bn_key + ".weight"] = dgamma[:c] * inv
-            grads[u.bn_key + ".bias"] = sum_dy[:c] * inv
+            emit(u.bn_key + ".weight", bn.weight, dgamma[:c] * inv)
+            emit(u.bn_key + ".bias", bn.bias, sum_dy[:c] * inv)
             A = gamma * u.invstd
             Bc = -A * u.invstd * (dgamma / u.rows)
             Cc = -A * (sum_dy / u.rows) - Bc * u.mean
@@ -205,9 +213,9 @@ class _ResnetTrainFn(torch.autograd.Function):
                 ci, co = node.weight.shape[0], node.weight.shape[1]
                 taps = [(ky - 1, kx - 1) for ky in range(4) for kx in range(4)]
                 rs = [(ky, kx) for ky in range(4) for kx in range(4)]
-                grads[u.conv_key + ".bias"] = ops.bias_grad(g)[:co] * inv
+                emit(u.conv_key + ".bias", node.bias, ops.bias_grad(g)[:co] * inv)
                 dw = ops.wgrad(g, u.x, taps, deconv=True)[:, :co, :ci]
-                grads[u.conv_key + ".weight"] = (dw * inv).permute(2, 1, 0).reshape(ci, co, 4, 4).contiguous()
+                emit(u.conv_key + ".weight", node.weight, (dw * inv).permute(2, 1, 0).reshape(ci, co, 4, 4))
                 wd = ops.pack_conv_weight(node.weight.detach(), rs, cin_pad=g.shape[3], cout_pad=u.x.shape[3])
                 B, H, W, _ = u.x.shape
                 dx = ops.conv_taps(g, wd, None, taps, H, W, stride=2)
@@ -217,7 +225,7 @@ class _ResnetTrainFn(torch.autograd.Function):
             elif u.kind == "first":
                 co = node.weight.shape[0]
                 dw = ops.wgrad(g, u.x, [(0, 0)])[0, :co, :147]                        # [co, (r,s,c)]
-                grads[u.conv_key + ".weight"] = (dw * inv).view(co, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+                emit(u.conv_key + ".weight", node.weight, (dw * inv).view(co, 7, 7, 3).permute(0, 3, 1, 2))
                 if cap is not None:
                     cap["cum_out"] = cum.clone()
             else:
@@ -235,7 +243,7 @@ class _ResnetTrainFn(torch.autograd.Function):
                 else:
                     dw = ops.wgrad_strided(g, u.x, taps)[:, :co, :ci]
                     dx = _dgrad_stride2(node.weight.detach(), g, u.x.shape)
-                grads[u.conv_key + ".weight"] = (dw * inv).permute(1, 2, 0).reshape(co, ci, ksz, ksz).contiguous()
+                emit(u.conv_key + ".weight", node.weight, (dw * inv).permute(1, 2, 0).reshape(co, ci, ksz, ksz))
                 if cap is not None:
                     cap["dx"], cap["cum_out"] = dx.clone(), cum.clone()
                 acc(u.x, dx)

@@ -220,6 +220,37 @@ constexpr int kStrip = 10;
 constexpr int kFusedThreads = 256;
 constexpr int kMaxMaskWords = 1024;          // h*w <= 32768 pixels
 
+// fp32 <-> fp64 conversions on the integer pipe.  On sm_100 F2F.F64.F32 / F2F.F32.F64 issue on the XU pipe at a few
+// threads per clock per SM: ncu showed the first version of this kernel with the XU pipe saturated (118 % of its
+// nominal peak) and the fp64 pipe 24 % busy -- the conversions, not the 74 fp64 operations per pixel, set its 190 us.
+// Both helpers are exact (widening is always exact; narrowing is IEEE round-to-nearest-even) for every finite normal
+// value and zero, and hand anything else (subnormal results, overflow, inf, nan) to the hardware instruction.
+// (out of line on purpose: inlined, the compiler predicates the F2F instead of branching around it)
+static __device__ __noinline__ double f2d_hw(float f) { return (double)f; }
+static __device__ __noinline__ float d2f_hw(double d) { return __double2float_rn(d); }
+__device__ __forceinline__ double f2d_exact(float f) {
+  const uint32_t b = __float_as_uint(f);
+  const uint32_t a = b & 0x7fffffffu;
+  if (a - 0x00800000u < 0x7f000000u) {                       // normal: exponent field 1..254
+    const uint32_t hi = (b & 0x80000000u) | ((a >> 3) + 0x38000000u);      // re-bias 127 -> 1023
+    return __hiloint2double((int)hi, (int)(b << 29));
+  }
+  if (a == 0) return __hiloint2double((int)b, 0);            // +-0
+  return f2d_hw(f);
+}
+__device__ __forceinline__ float d2f_rn(double d) {
+  const uint32_t hi = (uint32_t)__double2hiint(d), lo = (uint32_t)__double2loint(d);
+  const uint32_t e = (hi >> 20) & 0x7ffu;
+  if (e - 897u <= 1150u - 897u) {                            // result is a normal float before rounding
+    uint32_t f = (hi & 0x80000000u) | (((hi & 0x7fffffffu) - 0x38000000u) << 3) | (lo >> 29);
+    const uint32_t rem = lo & 0x1fffffffu;
+    f += (rem > 0x10000000u || (rem == 0x10000000u && (f & 1u))) ? 1u : 0u;   // a carry into the exponent is correct
+    return __uint_as_float(f);
+  }
+  if (((hi & 0x7fffffffu) | lo) == 0) return __uint_as_float(hi);             // +-0
+  return d2f_hw(d);
+}
+
 // One separable pass over a [n_other lines] x [n_axis samples] map.  Element (line o, sample i) of the source is
 // src[o*s_other + i*s_axis]; thread tasks are (strip, line) with the line index fastest, so that consecutive lanes
 // touch consecutive lines (the caller picks layouts where that is conflict free).  Arithmetic = gauss_pass_kernel's.
@@ -228,21 +259,22 @@ __device__ __forceinline__ void gauss_strips(const float* __restrict__ src, int 
                                              int n_other, const GaussW& gw) {
   const int strips = (n_axis + kStrip - 1) / kStrip;
   const int tasks = strips * n_other;
+  const uint32_t magic = 0xffffffffu / (uint32_t)n_other + 1u;      // t / n_other == umulhi(t, magic) for t*n_other < 2^32
   for (int t = threadIdx.x; t < tasks; t += kFusedThreads) {
-    const int strip = t / n_other;
+    const int strip = (int)__umulhi((uint32_t)t, magic);
     const int o = t - strip * n_other;
     const int c0 = strip * kStrip;
     const float* line = src + o * s_other;
     double v[kStrip + 2 * kFusedRadius];
     if (c0 >= kFusedRadius && c0 + kStrip + kFusedRadius <= n_axis) {
 #pragma unroll
-      for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) v[j] = (double)line[(c0 - kFusedRadius + j) * s_axis];
+      for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) v[j] = f2d_exact(line[(c0 - kFusedRadius + j) * s_axis]);
     } else {
 #pragma unroll
       for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) {
         int i = c0 - kFusedRadius + j;
         if (i < 0 || i >= n_axis) i = reflect_idx(i, n_axis);
-        v[j] = (double)line[i * s_axis];
+        v[j] = f2d_exact(line[i * s_axis]);
       }
     }
     float* out = dst + o * d_other + c0 * d_axis;
@@ -252,7 +284,7 @@ __device__ __forceinline__ void gauss_strips(const float* __restrict__ src, int 
 #pragma unroll
       for (int d = kFusedRadius; d >= 1; --d)
         acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[j + kFusedRadius - d], v[j + kFusedRadius + d]), gw.w[d]));
-      if (c0 + j < n_axis) out[j * d_axis] = __double2float_rn(acc);
+      if (c0 + j < n_axis) out[j * d_axis] = d2f_rn(acc);
     }
   }
 }
@@ -314,7 +346,8 @@ __device__ __forceinline__ Top2 top2_shfl_xor(const Top2& t, int m) {
 __global__ void __launch_bounds__(kFusedThreads, 2)
 peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, const __grid_constant__ GaussW gw,
                    double offset, int cap, double* __restrict__ peak_xy, float* __restrict__ peak_score,
-                   int32_t* __restrict__ peak_ij, int32_t* __restrict__ counts, double* __restrict__ summary) {
+                   int32_t* __restrict__ peak_ij, int32_t* __restrict__ counts, double* __restrict__ summary,
+                   float* __restrict__ smooth_out) {
   extern __shared__ __align__(16) float fsm[];
   const int hp = h | 1;                        // odd pitch of the transposed buffers
   const int total = h * w;
@@ -346,11 +379,20 @@ peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, con
     __syncthreads();
     // ---- peak test -> bitmask in raster order
     const float* sm = bufA;
+    const uint32_t wmagic = 0xffffffffu / (uint32_t)w + 1u;   // idx / w == umulhi(idx, wmagic): idx * w < 2^30
+    if (smooth_out != nullptr) {                              // dreamb200_gaussian_smooth: dump the filtered map, done
+      for (int idx = tid; idx < total; idx += kFusedThreads) {
+        const int py = (int)__umulhi((uint32_t)idx, wmagic), px = idx - py * w;
+        smooth_out[(long long)map * total + idx] = sm[px * hp + py];
+      }
+      __syncthreads();
+      continue;
+    }
     for (int base = wid * 32; base < words * 32; base += kFusedThreads) {
       const int idx = base + lane;
       bool is_peak = false;
       if (idx < total) {
-        const int py = idx / w, px = idx - py * w;
+        const int py = (int)__umulhi((uint32_t)idx, wmagic), px = idx - py * w;
         const float* c = sm + px * hp + py;
         const float v = c[0];
         const float up = py > 0 ? c[-1] : 0.0f;
@@ -390,7 +432,7 @@ peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, con
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
         const int idx = wd * 32 + b;
-        const int py = idx / w, px = idx - py * w;
+        const int py = (int)__umulhi((uint32_t)idx, wmagic), px = idx - py * w;
         double cx, cy;
         peak_centroid(mo, h, w, px, py, offset, &cx, &cy);
         const float score = __ldg(mo + idx);
@@ -427,6 +469,14 @@ peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, con
 }
 
 static size_t fused_smem_bytes(int h, int w) { return (size_t)2 * w * (h | 1) * sizeof(float); }
+static int fused_set_smem(size_t smem) {
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    DB_CHECK_CUDA(cudaFuncSetAttribute(peaks_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  return 0;
+}
 static bool fused_ok(int h, int w, int radius) {
   return radius == kFusedRadius && (long long)h * w <= 32LL * kMaxMaskWords && fused_smem_bytes(h, w) <= 200 * 1024;
 }
@@ -516,13 +566,9 @@ extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, cons
   for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
   if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) {
     const size_t smem = fused_smem_bytes(h, w);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      DB_CHECK_CUDA(cudaFuncSetAttribute(peaks_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
+    if (fused_set_smem(smem)) return -2;
     peaks_fused_kernel<<<n_maps, kFusedThreads, smem, stream>>>(maps, n_maps, h, w, gw, offset, cap, peak_xy,
-                                                                 peak_score, peak_ij, counts, summary);
+                                                                 peak_score, peak_ij, counts, summary, nullptr);
     DB_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -539,6 +585,32 @@ extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, cons
                                                           peak_ij, counts, summary);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch(3);
+  return 0;
+}
+
+extern "C" int dreamb200_gaussian_smooth(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
+                                         float* scratch, float* out, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  DB_REQUIRE(maps && gauss_w && out, "gaussian_smooth: null pointer");
+  DB_REQUIRE(n_maps > 0 && h > 0 && w > 0, "gaussian_smooth: empty input (n_maps=%d h=%d w=%d)", n_maps, h, w);
+  DB_REQUIRE(radius >= 0 && radius <= kMaxRadius, "gaussian_smooth: radius %d out of range", radius);
+  GaussW gw;
+  for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
+  if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) {
+    const size_t smem = fused_smem_bytes(h, w);
+    if (fused_set_smem(smem)) return -2;
+    peaks_fused_kernel<<<n_maps, kFusedThreads, smem, stream>>>(maps, n_maps, h, w, gw, 0.0, 1, nullptr, nullptr,
+                                                                 nullptr, nullptr, nullptr, out);
+  } else {
+    DB_REQUIRE(scratch, "gaussian_smooth: this map size / radius needs n_maps*h*w floats of scratch");
+    const long long total = (long long)n_maps * h * w;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)device_sm_count() * 32) blocks = (long long)device_sm_count() * 32;
+    gauss_pass_kernel<0><<<(int)blocks, 256, 0, stream>>>(maps, scratch, n_maps, h, w, gw, radius);
+    gauss_pass_kernel<1><<<(int)blocks, 256, 0, stream>>>(scratch, out, n_maps, h, w, gw, radius);
+  }
+  DB_CHECK_CUDA(cudaGetLastError());
+  count_launch(1);
   return 0;
 }
 

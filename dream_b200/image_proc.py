@@ -62,6 +62,26 @@ def find_peaks_device(maps, offset_due_to_upsampling, cap=64):
     return table
 
 
+def gaussian_smooth_device(maps, sigma=_SIGMA):
+    """scipy.ndimage.gaussian_filter(map, sigma) of every [h,w] map of a CUDA fp32 tensor, bit for bit (the smoothing
+    stage of `peaks_from_belief_maps`, image_proc.py:935, on its own)."""
+    assert maps.is_cuda and maps.dtype == torch.float32, "belief maps must be a CUDA fp32 tensor"
+    maps = maps.contiguous()
+    h, w = int(maps.shape[-2]), int(maps.shape[-1])
+    n_maps = maps.numel() // (h * w)
+    wts, radius = gaussian_half_kernel(sigma)
+    need = C.c_longlong(0)
+    check(lib().dreamb200_peaks_scratch_floats(n_maps, h, w, radius, C.byref(need)), "dreamb200_peaks_scratch_floats")
+    scratch = torch.empty((need.value // 2,), dtype=torch.float32, device=maps.device) if need.value else None
+    out = torch.empty_like(maps)
+    check(lib().dreamb200_gaussian_smooth(C.c_void_p(maps.data_ptr()), n_maps, h, w, wts.ctypes.data_as(C.c_void_p),
+                                          radius, C.c_void_p(scratch.data_ptr() if scratch is not None else 0),
+                                          C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "dreamb200_gaussian_smooth")
+    return out
+
+
 def peaks_from_belief_maps(belief_map_tensor, offset_due_to_upsampling):
     """Drop-in for dream/image_proc.py:914: [N,h,w] belief maps -> list[N] of list[(x, y, score, id)]
     (x, y Python floats; score np.float32; id running int), peaks in raster order."""

@@ -266,13 +266,26 @@ class DreamNetwork:
     def train(self, network_input_heads, target):
         assert self.optimizer, "Optimizer must be defined. Use enable_training() first."
         self.optimizer.zero_grad()
+        reducer = self._grad_reducer()
+        if reducer is not None:
+            reducer.begin_step()             # p.grad = views of the flat bucket buffer (zeroed)
         loss = self.loss(network_input_heads, target)
-        loss.backward()
-        if _distributed_world() > 1:
-            from .distributed import allreduce_gradients
-            allreduce_gradients(self.model)
+        loss.backward()                      # gradient buckets are all-reduced while backward is still running
+        if reducer is not None:
+            reducer.finish()
         self.optimizer.step()
         return loss
+
+    def _grad_reducer(self):
+        """Process-per-GPU replacement of DataParallel's gradient reduce (dream/network.py:244-256): created on the
+        first multi-rank `train()` call, together with the one-time parameter / buffer broadcast from rank 0."""
+        if _distributed_world() <= 1:
+            return None
+        if getattr(self, "_reducer", None) is None:
+            from .distributed import GradReducer, broadcast_parameters
+            broadcast_parameters(self.model)
+            self._reducer = GradReducer(self.model)
+        return self._reducer
 
     def loss(self, network_input_heads, target):
         if target.dim() == 3 and target.shape[-1] == 2:

@@ -127,6 +127,11 @@ int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* g
                     double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
 int dreamb200_peaks_scratch_floats(int n_maps, int h, int w, int radius, long long* n_floats);
+/* The smoothing stage of dreamb200_peaks alone: out[n_maps,h,w] = scipy.ndimage.gaussian_filter(map, sigma) bit for
+   bit (dream/image_proc.py:935; fp64 accumulation in scipy's tap order, "reflect" borders, one rounding to fp32 per
+   pass).  Same kernels as dreamb200_peaks; scratch (n_maps*h*w floats) only when the fused kernel does not apply. */
+int dreamb200_gaussian_smooth(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
+                              float* scratch, float* out, void* stream);
 
 /* ---- backward (training) ------------------------------------------------------------------ */
 /* dW[tap][co][ci] += sum_pixels dY[p][co] * X[p + tap][ci]; dy, x NHWC fp16 [B,H,W,Cout_pad|Cin_pad],

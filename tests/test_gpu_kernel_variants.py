@@ -83,6 +83,34 @@ def test_fused_peaks_equal_three_kernel_path_and_oracle(h, w, kind, built_lib):
         assert np.array_equal(fused["ij"][i, :c, 0], xs[:c]) and np.array_equal(fused["ij"][i, :c, 1], ys[:c]), i
 
 
+@pytest.mark.parametrize("h,w", [(100, 100), (37, 53), (7, 5), (120, 160)])
+def test_gaussian_smoothing_is_bit_exact_including_edge_values(h, w, built_lib):
+    """The smoothing stage alone against the oracle's scipy restatement, bit for bit, on values that exercise every
+    branch of the integer-pipe fp32<->fp64 conversions: normal numbers of both signs and all magnitudes, exact zeros,
+    fp32 subnormals (inputs and results), values near FLT_MAX."""
+    from dream_b200 import image_proc
+    rng = np.random.default_rng(h + w)
+    n = 12
+    maps = rng.standard_normal((n, h, w)).astype(np.float32)
+    maps[1] *= np.float32(1e-30)
+    maps[2] = (rng.standard_normal((h, w)) * 1e-40).astype(np.float32)              # subnormal inputs
+    maps[3] = 0.0
+    maps[4] = np.where(rng.random((h, w)) < 0.7, 0.0, maps[4])                      # mostly exact zeros
+    maps[5] *= np.float32(1e30)
+    maps[6] = np.float32(3e38) * np.sign(maps[6])                                   # near FLT_MAX, both signs
+    maps[7] = (10.0 ** rng.uniform(-44, 38, size=(h, w)) * np.sign(maps[7])).astype(np.float32)
+    maps[8] = np.float32(1.17549435e-38) * np.where(rng.random((h, w)) < 0.5, 1, -1)  # smallest normal: subnormal sums
+    maps[9, ::2] = 0.0
+    maps[9, 1::2] = np.float32(1e-45)                                               # smallest subnormal
+    want = np.stack([ref_peaks.gaussian_filter_f32(m) for m in maps])
+    dev = torch.from_numpy(maps).cuda()
+    for unfused in (None, "1"):
+        with env(DREAMB200_PEAKS_UNFUSED=unfused):
+            got = image_proc.gaussian_smooth_device(dev).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+            (unfused, np.argwhere(got.view(np.uint32) != want.view(np.uint32))[:5])
+
+
 def test_fused_peaks_full_batch_shape_matches_oracle_decisions(built_lib):
     """B=128 x 7 maps of 100x100 (the benchmarked shape) through the fused kernel: counts, refined coordinates and the
     keypoint decision equal the oracle's on a sample of the maps, and the two device paths agree on all of them."""
