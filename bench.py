@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--workload", default="vgg_q_infer", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="inference steps launched eagerly instead of graph replay")
     ap.add_argument("--layer-table", default=None, help="write per-layer timings (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -297,13 +298,20 @@ def main():
         targets = [torch.rand((B, K_KP, out_h, out_w), device=dev, generator=g) for _ in range(2)]
         host_t = [t.cpu().pin_memory() for t in targets]
 
+    # inference: the whole step (forward + peak extraction + decision table = DreamNetwork.inference_device) is
+    # captured once per input buffer into a CUDA graph (DreamNetwork.capture_inference) and replayed -- the same
+    # kernels, launched by one driver call instead of ~35 Python -> ctypes -> driver round trips.  --no-graph = eager.
+    graphs = None
+    if mode == "infer" and not args.no_graph:
+        graphs = [net.capture_inference(x, adopt=True) for x in xs]
+
     def step_device(i):
         if mode == "train":          # fwd + MSE + bwd + gradient all-reduce + Adam step (DreamNetwork.train)
             return net.train([xs[i & 1]], targets[i & 1])
+        if graphs is not None and ops.PROFILE is None:
+            return graphs[i & 1]()[1]
         with torch.no_grad():
-            belief = model.belief_maps(xs[i & 1])
-            table = image_proc.find_peaks_device(belief, offset)
-            return image_proc.select_keypoints_device(table, 0.25)
+            return net.inference_device(xs[i & 1])[1]
 
     # e2e: the public input pipeline (dream_b200.pipeline) around DreamNetwork.inference / .train: host (pinned)
     # batches in, keypoints (or the loss value) back on the host, H2D of step i+1 overlapped with step i.
@@ -342,6 +350,8 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - l0
+        if graphs is not None and not whole:          # replays do not pass through the library's launch counter
+            launches += steps * graphs[0].kernels_per_replay
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -430,6 +440,31 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.layer_table)), exist_ok=True)
             json.dump({"batch": B, "layers": table, "roofline": roof}, open(args.layer_table, "w"), indent=1)
 
+    # ---- single-image latency (A12: keypoints_from_image / the ROS loop): one 400x400 frame already on the device ->
+    # keypoints on the host, host-timed per call with a sync, eager launches vs the cached CUDA graph
+    latency = None
+    if rank == 0 and mode == "infer":
+        x1 = xs[0][:1].clone()
+
+        def lat(fn, n=40):
+            for _ in range(5):
+                fn()
+            ts = []
+            for _ in range(n):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            return ts[len(ts) // 2]
+        with torch.no_grad():
+            eager_ms = lat(lambda: net.inference(x1)[1])
+            graph_ms = lat(lambda: net.inference_graphed(x1)[1].cpu())
+        latency = {"batch": 1, "eager_ms": eager_ms, "cuda_graph_ms": graph_ms,
+                   "what": "DreamNetwork.inference on one %dx%d frame resident on the device -> [1,7,2] keypoints on "
+                           "the host; median of 40 host-timed calls" % (W, H)}
+
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "vgg_q_infer":
         ref_out = {}
@@ -465,6 +500,9 @@ def main():
             "cpu_baseline": cpu,
             "parity": parity,
             "allreduce": comm,
+            "latency_b1": latency,
+            "launch_mode": ("cuda graph replay, %d libdreamb200 kernels per step" % graphs[0].kernels_per_replay)
+            if graphs is not None else "eager",
         }
         print(json.dumps(line))
     if world > 1:

@@ -223,69 +223,85 @@ constexpr int kMaxMaskWords = 1024;          // h*w <= 32768 pixels
 // fp32 <-> fp64 conversions on the integer pipe.  On sm_100 F2F.F64.F32 / F2F.F32.F64 issue on the XU pipe at a few
 // threads per clock per SM: ncu showed the first version of this kernel with the XU pipe saturated (118 % of its
 // nominal peak) and the fp64 pipe 24 % busy -- the conversions, not the 74 fp64 operations per pixel, set its 190 us.
-// Both helpers are exact (widening is always exact; narrowing is IEEE round-to-nearest-even) for every finite normal
-// value and zero, and hand anything else (subnormal results, overflow, inf, nan) to the hardware instruction.
-// (out of line on purpose: inlined, the compiler predicates the F2F instead of branching around it)
-static __device__ __noinline__ double f2d_hw(float f) { return (double)f; }
-static __device__ __noinline__ float d2f_hw(double d) { return __double2float_rn(d); }
-__device__ __forceinline__ double f2d_exact(float f) {
+// A second version branched to the hardware instruction per value for the rare non-normal cases: 44 branch /
+// reconvergence pairs per task and a 160 KB unrolled body made it instruction-fetch bound (stall_no_inst on top).
+// Now both conversions are BRANCH-FREE bit manipulation, exact for normal numbers and zero (widening is always
+// exact; narrowing rounds to nearest even like the hardware), and each accumulates a flag when it meets anything else
+// (fp32 subnormal, inf, nan; a result outside the normal fp32 range).  A flagged task is simply recomputed by
+// gauss_task_exact with the hardware conversions -- one well-predicted branch per 10 outputs.
+__device__ __forceinline__ double f2d_fast(float f, uint32_t& flag) {
   const uint32_t b = __float_as_uint(f);
   const uint32_t a = b & 0x7fffffffu;
-  if (a - 0x00800000u < 0x7f000000u) {                       // normal: exponent field 1..254
-    const uint32_t hi = (b & 0x80000000u) | ((a >> 3) + 0x38000000u);      // re-bias 127 -> 1023
-    return __hiloint2double((int)hi, (int)(b << 29));
-  }
-  if (a == 0) return __hiloint2double((int)b, 0);            // +-0
-  return f2d_hw(f);
+  const bool normal = a - 0x00800000u < 0x7f000000u;                       // exponent field 1..254
+  flag |= normal ? 0u : a;                                                 // non-zero and not normal -> exact path
+  const uint32_t hi = (b & 0x80000000u) | (normal ? (a >> 3) + 0x38000000u : 0u);    // re-bias 127 -> 1023
+  return __hiloint2double((int)hi, (int)(b << 29));
 }
-__device__ __forceinline__ float d2f_rn(double d) {
+__device__ __forceinline__ float d2f_fast(double d, uint32_t& flag) {
   const uint32_t hi = (uint32_t)__double2hiint(d), lo = (uint32_t)__double2loint(d);
-  const uint32_t e = (hi >> 20) & 0x7ffu;
-  if (e - 897u <= 1150u - 897u) {                            // result is a normal float before rounding
-    uint32_t f = (hi & 0x80000000u) | (((hi & 0x7fffffffu) - 0x38000000u) << 3) | (lo >> 29);
-    const uint32_t rem = lo & 0x1fffffffu;
-    f += (rem > 0x10000000u || (rem == 0x10000000u && (f & 1u))) ? 1u : 0u;   // a carry into the exponent is correct
-    return __uint_as_float(f);
+  const uint32_t a = hi & 0x7fffffffu;
+  const bool normal = a - 0x38100000u < 0x0fe00000u;                       // exponent field 897..1150
+  flag |= normal ? 0u : (a | lo);                                          // non-zero and outside -> exact path
+  uint32_t f = ((a - 0x38000000u) << 3) | (lo >> 29);
+  const uint32_t rem = lo & 0x1fffffffu;
+  f += (rem > 0x10000000u || (rem == 0x10000000u && (f & 1u))) ? 1u : 0u; // a carry into the exponent is correct
+  return __uint_as_float((hi & 0x80000000u) | (normal ? f : 0u));
+}
+
+// Reference form of one task (the arithmetic of gauss_pass_kernel: hardware conversions, general reflection): used for
+// flagged tasks and for axes shorter than the register window.
+static __device__ __noinline__ void gauss_task_exact(const float* __restrict__ line, int s_axis,
+                                                     float* __restrict__ out_line, int d_axis, int c0, int n_axis,
+                                                     const GaussW& gw) {
+  for (int j = 0; j < kStrip && c0 + j < n_axis; ++j) {
+    const int c = c0 + j;
+    double acc = __dmul_rn((double)line[c * s_axis], gw.w[0]);
+    for (int d = kFusedRadius; d >= 1; --d) {
+      const int lo = reflect_idx(c - d, n_axis), hi = reflect_idx(c + d, n_axis);
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)line[lo * s_axis], (double)line[hi * s_axis]), gw.w[d]));
+    }
+    out_line[c * d_axis] = __double2float_rn(acc);
   }
-  if (((hi & 0x7fffffffu) | lo) == 0) return __uint_as_float(hi);             // +-0
-  return d2f_hw(d);
 }
 
 // One separable pass over a [n_other lines] x [n_axis samples] map.  Element (line o, sample i) of the source is
 // src[o*s_other + i*s_axis]; thread tasks are (strip, line) with the line index fastest, so that consecutive lanes
 // touch consecutive lines (the caller picks layouts where that is conflict free).  Arithmetic = gauss_pass_kernel's.
-__device__ __forceinline__ void gauss_strips(const float* __restrict__ src, int s_axis, int s_other,
-                                             float* __restrict__ dst, int d_axis, int d_other, int n_axis,
-                                             int n_other, const GaussW& gw) {
+// Out of line: both passes share one copy of the unrolled body (instruction cache).
+static __device__ __noinline__ void gauss_strips(const float* __restrict__ src, int s_axis, int s_other,
+                                                 float* __restrict__ dst, int d_axis, int d_other, int n_axis,
+                                                 int n_other, const GaussW& gw) {
   const int strips = (n_axis + kStrip - 1) / kStrip;
   const int tasks = strips * n_other;
   const uint32_t magic = 0xffffffffu / (uint32_t)n_other + 1u;      // t / n_other == umulhi(t, magic) for t*n_other < 2^32
+  const bool windowed = n_axis >= kStrip + 2 * kFusedRadius;        // one reflection per side is enough
   for (int t = threadIdx.x; t < tasks; t += kFusedThreads) {
     const int strip = (int)__umulhi((uint32_t)t, magic);
     const int o = t - strip * n_other;
     const int c0 = strip * kStrip;
     const float* line = src + o * s_other;
-    double v[kStrip + 2 * kFusedRadius];
-    if (c0 >= kFusedRadius && c0 + kStrip + kFusedRadius <= n_axis) {
-#pragma unroll
-      for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) v[j] = f2d_exact(line[(c0 - kFusedRadius + j) * s_axis]);
-    } else {
+    float* out_line = dst + o * d_other;
+    uint32_t flag = windowed ? 0u : 1u;
+    if (windowed) {
+      double v[kStrip + 2 * kFusedRadius];
 #pragma unroll
       for (int j = 0; j < kStrip + 2 * kFusedRadius; ++j) {
         int i = c0 - kFusedRadius + j;
-        if (i < 0 || i >= n_axis) i = reflect_idx(i, n_axis);
-        v[j] = f2d_exact(line[i * s_axis]);
+        i = i < 0 ? -1 - i : i;                                     // "reflect": d c b a | a b c d | d c b a
+        i = i >= n_axis ? 2 * n_axis - 1 - i : i;
+        v[j] = f2d_fast(line[i * s_axis], flag);
+      }
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) {
+        double acc = __dmul_rn(v[j + kFusedRadius], gw.w[0]);
+#pragma unroll
+        for (int d = kFusedRadius; d >= 1; --d)
+          acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[j + kFusedRadius - d], v[j + kFusedRadius + d]), gw.w[d]));
+        const float r = d2f_fast(acc, flag);
+        if (c0 + j < n_axis) out_line[(c0 + j) * d_axis] = r;
       }
     }
-    float* out = dst + o * d_other + c0 * d_axis;
-#pragma unroll
-    for (int j = 0; j < kStrip; ++j) {
-      double acc = __dmul_rn(v[j + kFusedRadius], gw.w[0]);
-#pragma unroll
-      for (int d = kFusedRadius; d >= 1; --d)
-        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[j + kFusedRadius - d], v[j + kFusedRadius + d]), gw.w[d]));
-      if (c0 + j < n_axis) out[j * d_axis] = d2f_rn(acc);
-    }
+    if (flag != 0u) gauss_task_exact(line, s_axis, out_line, d_axis, c0, n_axis, gw);
   }
 }
 

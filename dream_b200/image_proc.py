@@ -119,8 +119,9 @@ def select_keypoints_device(table, next_best_score, sentinel=-999.999):
     cnt = table.counts
     s = table.summary
     gap = s[:, 2].float() - s[:, 3].float()
-    take = (cnt == 1) | ((cnt > 1) & (gap >= torch.tensor(next_best_score, dtype=torch.float32,
-                                                          device=gap.device)))
+    # (a Python scalar, not torch.tensor(..., device=cuda): that would be a pageable H2D copy, illegal while a CUDA
+    # graph is being captured; the comparison still happens in fp32 against float32(next_best_score))
+    take = (cnt == 1) | ((cnt > 1) & (gap >= float(np.float32(next_best_score))))
     # torch.where, not boolean-mask assignment: no data-dependent shape, hence no hidden host sync
     return torch.where(take.unsqueeze(1), s[:, :2], torch.full_like(s[:, :2], sentinel))
 

@@ -193,6 +193,8 @@ class DreamNetwork:
 
         self.use_belief_peak_scores = True
         self.belief_peak_next_best_score = 0.25
+        # single-image path through a captured CUDA graph (DREAMB200_GRAPHS=0: always eager)
+        self.use_cuda_graphs = os.environ.get("DREAMB200_GRAPHS", "1") != "0"
 
         # ---- model (dream/network.py:194-298) ----
         if self.architecture_type == "vgg":
@@ -343,7 +345,13 @@ class DreamNetwork:
         std = np.asarray(self.image_normalization["stdev"], dtype=np.float32)
         x = torch.from_numpy(np.ascontiguousarray(((arr - mean) / std).transpose(2, 0, 1)))
         with torch.no_grad():
-            belief_batch, kp_batch = self.inference(x.unsqueeze(0).to(self.device))
+            xin = x.unsqueeze(0).to(self.device)
+            if self.use_cuda_graphs and self.network_config["architecture"]["output_heads"] == ["belief_maps"]:
+                # B = 1 latency path: ~35 launches replayed as one CUDA graph per input resolution
+                belief_batch, kps_dev = self.inference_graphed(xin)
+                kp_batch = kps_dev.cpu().float()
+            else:
+                belief_batch, kp_batch = self.inference(xin)
         belief_maps_net_out = belief_batch[0]
         detected_kp_projs_net_out = np.array(kp_batch[0], dtype=float)
         belief_map = belief_maps_net_out[0]
@@ -373,6 +381,36 @@ class DreamNetwork:
         """`inference` without the final host copy: (belief maps [B,K,h,w] cuda, keypoints [B,K,2] float64 cuda).
         Nothing here synchronises with the host, so callers can queue the next batch before reading this one
         (dream_b200.pipeline.inference_stream does)."""
+        return self._inference_device_eager(network_input)
+
+    # ---- whole-step CUDA graphs (dream_b200/graph.py) ------------------------------------------
+    cuda_graph_cache_size = 4
+
+    def capture_inference(self, network_input, adopt=False):
+        """Capture `inference_device` for this input's shape / dtype and the current weights into a CUDA graph and
+        return the `InferenceGraph` (callable: `belief, kps = g(x)`).  With `adopt=True` the graph reads straight
+        from `network_input`'s buffer: refill it in place and call `g()`."""
+        from .graph import InferenceGraph
+        assert self.network_config["architecture"]["output_heads"] == ["belief_maps"], \
+            "graph capture covers the belief-map inference path"
+        return InferenceGraph(self, network_input, adopt=adopt)
+
+    def inference_graphed(self, network_input):
+        """`inference_device` through a cached CUDA graph keyed on (shape, dtype, weights version): the first call per
+        key captures, later calls copy the batch into the graph's input buffer and replay.  Outputs are cloned, so
+        they stay valid like eager results.  Used by `keypoints_from_image` (B = 1 latency path)."""
+        from .graph import graph_key
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        key = graph_key(self, network_input)
+        g = cache.get(key)
+        if g is None:
+            if len(cache) >= self.cuda_graph_cache_size:
+                cache.pop(next(iter(cache)))
+            g = cache[key] = self.capture_inference(network_input)
+        belief, kps = g(network_input)
+        return belief.clone(), kps.clone()
+
+    def _inference_device_eager(self, network_input):
         belief_maps_batch = self.model(network_input)[-1]
         tw, th = self.trained_net_output_resolution()
         offset = 0.0 if (tw >= 400 and th >= 400) else 0.4395     # network.py:534-538

@@ -213,3 +213,48 @@ def test_wgrad_pair_kernel_matches_single_cta_and_autograd(B, H, W, Ci, Co, buil
     torch.nn.functional.conv2d(xr, wz, padding=1).backward(dy.permute(0, 3, 1, 2).float())
     ref = wz.grad.permute(2, 3, 0, 1).reshape(9, Co, Ci)
     assert (pair - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_cuda_graph_inference_is_bit_identical_to_eager_and_follows_the_weights(built_lib):
+    """DreamNetwork.capture_inference / inference_graphed (the whole step as one CUDA graph) against the eager launches:
+    same kernels on the same data -> identical bits; new weights or a new shape -> a new capture, not a stale replay."""
+    from conftest import panda_config
+    from dream_b200 import network
+    from oracle import ref_models
+    net = network.create_network_from_config_data(panda_config("vgg"))
+    net.enable_evaluation()
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=3, out_gain=13.0, mode="default")
+    net.model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1)
+    xa = (torch.rand((3, 3, 96, 128), generator=g) * 2 - 1).cuda()
+    xb = (torch.rand((3, 3, 96, 128), generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        for x in (xa, xb, xa):
+            be, ke = net.inference_device(x)
+            bg, kg = net.inference_graphed(x)
+            assert torch.equal(be, bg) and torch.equal(ke, kg)
+        assert len(net._graph_cache) == 1
+        graph = next(iter(net._graph_cache.values()))
+        assert graph.replays == 3 and graph.kernels_per_replay >= 20
+        # explicit capture on the caller's buffer: refill in place, replay
+        buf = xa.clone()
+        cap = net.capture_inference(buf, adopt=True)
+        buf.copy_(xb)
+        b2, k2 = cap()
+        be, ke = net.inference_device(xb)
+        assert torch.equal(b2, be) and torch.equal(k2, ke)
+        # another shape -> another graph; new weights -> the old graph is not reused
+        xc = (torch.rand((1, 3, 64, 64), generator=g) * 2 - 1).cuda()
+        assert torch.equal(net.inference_graphed(xc)[0], net.inference_device(xc)[0])
+        sd2 = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=4, out_gain=13.0, mode="default")
+        net.model.load_state_dict(sd2)
+        be, ke = net.inference_device(xa)
+        bg, kg = net.inference_graphed(xa)
+        assert torch.equal(be, bg) and torch.equal(ke, kg) and not torch.equal(be, b2)
+    # the single-image facade goes through the graph by default and must agree with the eager facade
+    from PIL import Image
+    img = Image.fromarray((np.random.default_rng(0).random((480, 640, 3)) * 255).astype(np.uint8))
+    ra = net.keypoints_from_image(img)
+    net.use_cuda_graphs = False
+    rb = net.keypoints_from_image(img)
+    assert np.array_equal(ra["detected_keypoints"], rb["detected_keypoints"])
