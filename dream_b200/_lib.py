@@ -65,9 +65,12 @@ _PROTOS = {
                                [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dreamb200_wgrad_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 +
                                 [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "dreamb200_bn_stats_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "dreamb200_bn_reduce_workspace": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "dreamb200_bn_stats_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "dreamb200_bn_apply_f16": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
-    "dreamb200_bn_bwd_reduce_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "dreamb200_bn_bwd_reduce_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                                                               C.c_void_p]),
     "dreamb200_bn_bwd_apply_f16": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
     "dreamb200_maxpool3_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dreamb200_scale_mask_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),

@@ -780,9 +780,43 @@ __global__ void bias_grad_kernel(const __half* __restrict__ dy, float* __restric
 }
 
 // ---- BatchNorm2d in training mode (torchvision ResNet trunk + decoder BNs, models.py:22-32,46-76) ----
-// per-channel sum and sum of squares of z [rows, C] fp16 (fp32 accumulation, fp32 atomics; caller zeroes outputs)
+// Deterministic two-stage column reduction shared by bn_stats and bn_bwd_reduce: every block writes its 2 x 64 partial
+// sums to `partials[which][block][C]`, takes a ticket on `tickets[channel group]`, and the block that draws the LAST
+// ticket adds the partials in block order and WRITES the result (no floating-point atomics: the summation order, and
+// with it the batch statistics and every ReLU decision downstream, is the same on every run -- the reference gets
+// this from cudnn.deterministic, dream/utilities.py:15-26).  The winner also re-arms the ticket for the next launch.
+__device__ __forceinline__ void two_stage_finish(float (*sh)[8][64], float* __restrict__ partials,
+                                                 unsigned* __restrict__ tickets, float* __restrict__ out0,
+                                                 float* __restrict__ out1, int C) {
+  const int cg = blockIdx.y;
+  const int nb = gridDim.x;
+  __shared__ bool last;
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += sh[which][i][ch];
+    partials[((size_t)which * nb + blockIdx.x) * C + cg * 64 + ch] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + cg, 1u) == (unsigned)nb - 1u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    const float* p = partials + (size_t)which * nb * C + cg * 64 + ch;
+    float v = 0.f;
+    for (int b = 0; b < nb; ++b) v += __ldcg(p + (size_t)b * C);
+    (which ? out1 : out0)[cg * 64 + ch] = v;
+  }
+  if (threadIdx.x == 0) tickets[cg] = 0u;
+}
+
+// per-channel sum and sum of squares of z [rows, C] fp16 (fp32 accumulation, fixed summation order)
 __global__ void bn_stats_kernel(const __half* __restrict__ z, float* __restrict__ sum, float* __restrict__ sumsq,
-                                long long rows, int C) {
+                                long long rows, int C, float* __restrict__ partials, unsigned* __restrict__ tickets) {
   const int cg = blockIdx.y;
   const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
   const int c = cg * 64 + tc * 2;
@@ -795,13 +829,7 @@ __global__ void bn_stats_kernel(const __half* __restrict__ z, float* __restrict_
   sh[0][tr][tc * 2] = a0; sh[0][tr][tc * 2 + 1] = a1;
   sh[1][tr][tc * 2] = q0; sh[1][tr][tc * 2 + 1] = q1;
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v += sh[which][i][ch];
-    atomicAdd((which ? sumsq : sum) + cg * 64 + ch, v);
-  }
+  two_stage_finish(sh, partials, tickets, sum, sumsq, C);
 }
 
 // y = relu?( z * scale[c] + shift[c] (+ residual) ), fp16 in / out, 8 channels per thread
@@ -831,9 +859,10 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ z, const float* __rest
   }
 }
 
-// BN backward reductions: sum_dy[c] += sum dy, sum_dyz[c] += sum dy * z   (dy already ReLU-masked)
+// BN backward reductions: sum_dy[c] = sum dy, sum_dyz[c] = sum dy * z   (dy already ReLU-masked; fixed order)
 __global__ void bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ z,
-                                     float* __restrict__ sum_dy, float* __restrict__ sum_dyz, long long rows, int C) {
+                                     float* __restrict__ sum_dy, float* __restrict__ sum_dyz, long long rows, int C,
+                                     float* __restrict__ partials, unsigned* __restrict__ tickets) {
   const int cg = blockIdx.y;
   const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
   const int c = cg * 64 + tc * 2;
@@ -847,13 +876,7 @@ __global__ void bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half
   sh[0][tr][tc * 2] = a0; sh[0][tr][tc * 2 + 1] = a1;
   sh[1][tr][tc * 2] = q0; sh[1][tr][tc * 2 + 1] = q1;
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v += sh[which][i][ch];
-    atomicAdd((which ? sum_dyz : sum_dy) + cg * 64 + ch, v);
-  }
+  two_stage_finish(sh, partials, tickets, sum_dy, sum_dyz, C);
 }
 
 // dz = a[c] * dy + b[c] * z + c0[c]   (BN backward, coefficients precomputed per channel), in place on dy
@@ -1145,10 +1168,18 @@ static dim3 reduce_grid(long long rows, int C) {
   return dim3((unsigned)bx, (unsigned)(C / 64));
 }
 
-extern "C" int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, void* stream) {
-  DB_REQUIRE(z && sum && sumsq && rows > 0 && C % 64 == 0, "bn_stats: bad arguments");
+extern "C" int dreamb200_bn_reduce_workspace(long long rows, int C, long long* partial_floats, int* n_tickets) {
+  DB_REQUIRE(partial_floats && n_tickets && rows > 0 && C % 64 == 0, "bn_reduce_workspace: bad arguments");
+  *partial_floats = 2LL * reduce_grid(rows, C).x * C;
+  *n_tickets = C / 64;
+  return 0;
+}
+
+extern "C" int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, float* partials,
+                                      unsigned* tickets, void* stream) {
+  DB_REQUIRE(z && sum && sumsq && partials && tickets && rows > 0 && C % 64 == 0, "bn_stats: bad arguments");
   bn_stats_kernel<<<reduce_grid(rows, C), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(z), sum,
-                                                                          sumsq, rows, C);
+                                                                          sumsq, rows, C, partials, tickets);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1167,10 +1198,12 @@ extern "C" int dreamb200_bn_apply_f16(const void* z, const float* scale, const f
 }
 
 extern "C" int dreamb200_bn_bwd_reduce_f16(const void* dy, const void* z, float* sum_dy, float* sum_dyz, long long rows,
-                                           int C, void* stream) {
-  DB_REQUIRE(dy && z && sum_dy && sum_dyz && rows > 0 && C % 64 == 0, "bn_bwd_reduce: bad arguments");
+                                           int C, float* partials, unsigned* tickets, void* stream) {
+  DB_REQUIRE(dy && z && sum_dy && sum_dyz && partials && tickets && rows > 0 && C % 64 == 0,
+             "bn_bwd_reduce: bad arguments");
   bn_bwd_reduce_kernel<<<reduce_grid(rows, C), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(z), sum_dy, sum_dyz, rows, C);
+      reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(z), sum_dy, sum_dyz, rows, C, partials,
+      tickets);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -407,12 +407,27 @@ def wgrad_strided(dy, x, taps):
     return dw
 
 
+_BN_TICKETS = {}
+
+
+def _bn_workspace(rows, Cc, device):
+    """(partials, tickets) for the deterministic two-stage reductions: scratch partial sums and the persistent,
+    always-zero-between-launches ticket counters of this device (dreamb200_bn_reduce_workspace)."""
+    nf, nt = C.c_longlong(0), C.c_int(0)
+    check(lib().dreamb200_bn_reduce_workspace(rows, Cc, C.byref(nf), C.byref(nt)), "dreamb200_bn_reduce_workspace")
+    tickets = _BN_TICKETS.get(device)
+    if tickets is None or tickets.numel() < nt.value:
+        tickets = _BN_TICKETS[device] = torch.zeros((max(64, nt.value),), dtype=torch.int32, device=device)
+    return torch.empty((nf.value,), dtype=torch.float32, device=device), tickets
+
+
 def bn_stats(z):
-    """Per-channel (sum, sum of squares) of an fp16 NHWC tensor, fp32 [C] each."""
+    """Per-channel (sum, sum of squares) of an fp16 NHWC tensor, fp32 [C] each (fixed summation order)."""
     Cc = z.shape[-1]
-    s = torch.zeros((2, Cc), dtype=torch.float32, device=z.device)
-    check(lib().dreamb200_bn_stats_f16(_ptr(z), _ptr(s[0]), _ptr(s[1]), z.numel() // Cc, Cc, _stream()),
-          "dreamb200_bn_stats_f16")
+    s = torch.empty((2, Cc), dtype=torch.float32, device=z.device)
+    partials, tickets = _bn_workspace(z.numel() // Cc, Cc, z.device)
+    check(lib().dreamb200_bn_stats_f16(_ptr(z), _ptr(s[0]), _ptr(s[1]), z.numel() // Cc, Cc, _ptr(partials),
+                                       _ptr(tickets), _stream()), "dreamb200_bn_stats_f16")
     return s[0], s[1]
 
 
@@ -426,9 +441,10 @@ def bn_apply(z, scale, shift, residual=None, relu=False):
 
 def bn_bwd_reduce(dy, z):
     Cc = z.shape[-1]
-    s = torch.zeros((2, Cc), dtype=torch.float32, device=z.device)
+    s = torch.empty((2, Cc), dtype=torch.float32, device=z.device)
+    partials, tickets = _bn_workspace(z.numel() // Cc, Cc, z.device)
     check(lib().dreamb200_bn_bwd_reduce_f16(_ptr(dy), _ptr(z), _ptr(s[0]), _ptr(s[1]), z.numel() // Cc, Cc,
-                                            _stream()), "dreamb200_bn_bwd_reduce_f16")
+                                            _ptr(partials), _ptr(tickets), _stream()), "dreamb200_bn_bwd_reduce_f16")
     return s[0], s[1]
 
 

@@ -148,14 +148,20 @@ int dreamb200_wgrad_strided(const void* dy, const void* x, float* dw, int B, int
                             int Cout_pad, int Cin_pad, int taps, const int8_t* tap_dy, const int8_t* tap_dx,
                             void* stream);
 /* nn.BatchNorm2d in training mode (ResNet trunk / decoder, models.py:22-32,46-76), z fp16 [rows, C]:
-   bn_stats: sum[c] += sum_rows z, sumsq[c] += sum_rows z^2 (caller zeroes; C % 64 == 0);
+   bn_stats: sum[c] = sum_rows z, sumsq[c] = sum_rows z^2 (C % 64 == 0);
    bn_apply: y = relu?(z*scale[c] + shift[c] (+ residual)) fp16;
-   bn_bwd_reduce: sum_dy[c] += sum dy, sum_dyz[c] += sum dy*z;  bn_bwd_apply: dy = a[c]*dy + b[c]*z + c0[c] in place */
-int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, void* stream);
+   bn_bwd_reduce: sum_dy[c] = sum dy, sum_dyz[c] = sum dy*z;  bn_bwd_apply: dy = a[c]*dy + b[c]*z + c0[c] in place.
+   The two reductions are DETERMINISTIC (two-stage, fixed summation order, no floating-point atomics -- what
+   cudnn.deterministic gives the reference, dream/utilities.py:15-26): `partials` is scratch of
+   dreamb200_bn_reduce_workspace() floats (contents irrelevant), `tickets` n_tickets uint32 that must be ZERO on
+   entry and are zero again on exit (one persistent buffer serves every launch on a stream). */
+int dreamb200_bn_reduce_workspace(long long rows, int C, long long* partial_floats, int* n_tickets);
+int dreamb200_bn_stats_f16(const void* z, float* sum, float* sumsq, long long rows, int C, float* partials,
+                           unsigned* tickets, void* stream);
 int dreamb200_bn_apply_f16(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                            long long rows, int C, int relu, void* stream);
 int dreamb200_bn_bwd_reduce_f16(const void* dy, const void* z, float* sum_dy, float* sum_dyz, long long rows, int C,
-                                void* stream);
+                                float* partials, unsigned* tickets, void* stream);
 int dreamb200_bn_bwd_apply_f16(void* dy, const void* z, const float* a, const float* b, const float* c0,
                                long long rows, int C, void* stream);
 /* autograd of MaxPool2d(3, stride 2, padding 1) (resnet stem): x [B,H,W,C], dy [B,(H-1)/2+1,(W-1)/2+1,C] */
