@@ -8,8 +8,10 @@ here and vice versa:
   * the rolling pickle `training_log_e{N}.pkl`, renamed to `training_log.pkl` when training ends (:641-665);
   * resume (:66-147, :326-407): newest `epoch_*.pth`, best validation loss from `best_network.yaml`, random seed from the
     training log, and a list of config keys that must not have changed.
-One file is added that the reference does not have: `epoch_{N}.optim.pth` with the optimizer state (the reference
-restarts Adam's moments on every resume).  It is optional on both sides: absent -> the reference's behaviour.
+One file is added that the reference does not have: `optim_epoch_{N}.pt` with the optimizer state (the reference
+restarts Adam's moments on every resume).  It is optional on both sides: absent -> the reference's behaviour.  The name
+is chosen so that the reference's resume scan (train_network.py:70-85: every file that starts with "epoch" and ends
+with ".pth" is taken for a weights file) can never pick it up.
 
 `AsyncCheckpointWriter` takes the device -> host copy and the `torch.save` off the training thread: the state dict is
 snapshotted into pinned host buffers on a side stream (the next step's kernels are not blocked) and written by a worker
@@ -44,6 +46,10 @@ def list_epoch_checkpoints(output_dir):
             found.append((int(m.group(1)), path, path[:-4] + ".yaml"))
     found.sort(key=lambda t: t[0], reverse=True)
     return found
+
+
+def optimizer_state_path(output_dir, epoch):
+    return os.path.join(output_dir, "optim_epoch_{}.pt".format(epoch))
 
 
 def assert_resume_consistent(saved_config, new_config):
@@ -111,7 +117,7 @@ def find_resume_point(output_dir, new_network_config=None, total_epochs=None, lo
     if new_network_config is not None:
         assert_resume_consistent(saved, new_network_config)
     log = load_training_log(output_dir, start_epoch) if load_log else None
-    optim_path = weights_path[:-4] + ".optim.pth"
+    optim_path = optimizer_state_path(output_dir, start_epoch)
     return ResumePoint(start_epoch, weights_path, config_path, saved, best, log,
                        optim_path if os.path.exists(optim_path) else None)
 
@@ -146,12 +152,13 @@ def save_epoch(network, output_dir, epoch, train_log=None, previous_epoch=None, 
         _write_log(output_dir, epoch, train_log, previous_epoch)
     optim_state = network.optimizer.state_dict() if (save_optimizer and network.optimizer is not None) else None
     if writer is not None:
-        writer.submit(network.model.state_dict(), network.network_config, output_dir, names, optim_state)
+        writer.submit(network.model.state_dict(), network.network_config, output_dir, names, optim_state,
+                      optim_path=optimizer_state_path(output_dir, epoch))
         return
     for name in names:
         network.save_network(output_dir, name, overwrite=True)
     if optim_state is not None:
-        torch.save(optim_state, os.path.join(output_dir, names[0] + ".optim.pth"))
+        torch.save(optim_state, optimizer_state_path(output_dir, epoch))
 
 
 def finish_training(output_dir, last_epoch):
@@ -162,14 +169,15 @@ def finish_training(output_dir, last_epoch):
 
 
 def _snapshot(obj, stream):
-    """Deep copy of a (nested) state dict with every tensor in host memory; CUDA tensors are copied asynchronously on
-    `stream` into pinned buffers."""
+    """Deep copy of a (nested) state dict with every tensor in host memory.  A CUDA tensor is first CLONED on the
+    current (training) stream -- `state_dict()` / `optimizer.state_dict()` alias the live parameters, Adam moments and
+    BatchNorm buffers, which the next step updates in place -- and the clone is then copied to a pinned buffer on
+    `stream`; the caller makes `stream` wait for the clones before the copies start."""
     if torch.is_tensor(obj):
         if obj.is_cuda:
+            frozen = obj.detach().clone()                         # ordered before the next step's in-place updates
             host = torch.empty(obj.shape, dtype=obj.dtype, device="cpu", pin_memory=True)
-            with torch.cuda.stream(stream):
-                host.copy_(obj, non_blocking=True)
-            return host
+            return _Pending(frozen, host)
         return obj.detach().clone()
     if isinstance(obj, dict):
         return type(obj)((k, _snapshot(v, stream)) for k, v in obj.items())
@@ -178,10 +186,34 @@ def _snapshot(obj, stream):
     return obj
 
 
+class _Pending:
+    """A device clone waiting for its device -> host copy."""
+    __slots__ = ("dev", "host")
+
+    def __init__(self, dev, host):
+        self.dev, self.host = dev, host
+
+
+def _drain(obj, stream):
+    """Second pass of a snapshot: issue the device -> host copies on `stream` and return the structure with the
+    pinned host tensors in place of the `_Pending` markers."""
+    if isinstance(obj, _Pending):
+        with torch.cuda.stream(stream):
+            obj.host.copy_(obj.dev, non_blocking=True)
+            obj.dev.record_stream(stream)                         # the clone may be freed only after the copy
+        return obj.host
+    if isinstance(obj, dict):
+        return type(obj)((k, _drain(v, stream)) for k, v in obj.items())
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_drain(v, stream) for v in obj)
+    return obj
+
+
 class AsyncCheckpointWriter:
-    """Writes checkpoints on a worker thread.  `submit` snapshots the tensors (device -> pinned host on a side stream
-    that first waits for the training stream, so the snapshot is the state after the step that was just queued) and
-    returns; the worker waits for the copies and writes the same files `DreamNetwork.save_network` writes."""
+    """Writes checkpoints on a worker thread.  `submit` freezes the tensors with device-side clones on the training
+    stream (the state after the step that was just queued; later in-place updates cannot tear it), copies the clones to
+    pinned host buffers on a side stream and returns; the worker waits for the copies and writes the same files
+    `DreamNetwork.save_network` writes."""
 
     def __init__(self):
         self._q = queue.Queue()
@@ -190,18 +222,25 @@ class AsyncCheckpointWriter:
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
-    def submit(self, state_dict, network_config, output_dir, names, optim_state=None):
+    def submit(self, state_dict, network_config, output_dir, names, optim_state=None, optim_path=None):
         self._raise_pending()
         done = None
-        if self._stream is not None:
-            self._stream.wait_stream(torch.cuda.current_stream())
+        # 1. freeze: device-side clones on the training stream (cheap, ordered before any later in-place update)
         weights = _snapshot(state_dict, self._stream)
         optim = _snapshot(optim_state, self._stream) if optim_state is not None else None
         if self._stream is not None:
+            # 2. copy out on the side stream once the clones exist; the training stream never waits for this
+            self._stream.wait_stream(torch.cuda.current_stream())
+            weights = _drain(weights, self._stream)
+            optim = _drain(optim, self._stream) if optim is not None else None
             done = torch.cuda.Event()
             done.record(self._stream)
         config = pickle.loads(pickle.dumps(network_config))      # the caller keeps mutating training.results
-        self._q.put((weights, optim, config, output_dir, list(names), done))
+        if optim is not None and optim_path is None:
+            m = re.match(r"^epoch_(\d+)$", names[0])
+            optim_path = optimizer_state_path(output_dir, int(m.group(1))) if m else \
+                os.path.join(output_dir, "optim_" + names[0] + ".pt")
+        self._q.put((weights, optim, config, output_dir, list(names), done, optim_path))
 
     def _run(self):
         while True:
@@ -210,14 +249,14 @@ class AsyncCheckpointWriter:
                 self._q.task_done()
                 return
             try:
-                weights, optim, config, output_dir, names, done = item
+                weights, optim, config, output_dir, names, done, optim_path = item
                 if done is not None:
                     done.synchronize()
                 for name in names:
                     dump_yaml_config(config, os.path.join(output_dir, name + ".yaml"))
                     torch.save(weights, os.path.join(output_dir, name + ".pth"))
                 if optim is not None:
-                    torch.save(optim, os.path.join(output_dir, names[0] + ".optim.pth"))
+                    torch.save(optim, optim_path)
             except Exception as e:  # surfaced on the next submit / wait
                 self._err = e
             finally:

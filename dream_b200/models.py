@@ -292,6 +292,10 @@ class DreamHourglass(_PlanModule):
         _add_conv(self, "heads_0.0", 64, 64, 3)
         _add_conv(self, "heads_0.2", 64, 32, 3)
         _add_conv(self, "heads_0.4", 32, n_keypoints, 3)
+        # the reference's trunk is torchvision's pretrained VGG-19 (models.py:587); taken from a LOCAL checkpoint when
+        # there is one, otherwise random with a warning (dream_b200/pretrained.py) -- never downloaded
+        from . import pretrained as _pretrained
+        _pretrained.load_vgg19_trunk(self)
         if internalize_spatial_softmax:
             from .spatial_softmax import SoftArgmaxPavlo
             self.softmax = nn.Sequential()
@@ -510,6 +514,11 @@ class ResnetSimple(_PlanModule):
             _add_conv(self, "upsample2.3", 256, n_keypoints, 1)
         else:
             _add_conv(self, "upsample.12", 256, n_keypoints, 1)
+        # `freeze` is accepted and ignored exactly like the reference's (models.py:18-21 never reads it);
+        # `pretrained=True` takes torchvision's resnet101 weights from a LOCAL checkpoint (dream_b200/pretrained.py)
+        if pretrained:
+            from . import pretrained as _pretrained
+            _pretrained.load_resnet101_trunk(self)
 
     def _n(self, key):
         return _node_for(self, key)

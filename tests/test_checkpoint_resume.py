@@ -57,13 +57,25 @@ def test_epoch_files_follow_the_reference_contract_and_resume_restores_everythin
         checkpoint.save_epoch(net, out, epoch, train_log=log, previous_epoch=epoch - 1, is_best=True)
     files = set(os.listdir(out))
     assert {"epoch_1.pth", "epoch_1.yaml", "epoch_3.pth", "epoch_3.yaml", "best_network.pth", "best_network.yaml",
-            "epoch_3.optim.pth", "training_log_e3.pkl"} <= files
+            "optim_epoch_3.pt", "training_log_e3.pkl"} <= files
     assert "training_log_e2.pkl" not in files                       # rolling log (train_network.py:647-653)
     assert all(k.startswith("module.") for k in torch.load(os.path.join(out, "epoch_3.pth")))
     checkpoint.finish_training(out, 3)
     assert os.path.exists(os.path.join(out, "training_log.pkl"))
 
     assert [c[0] for c in checkpoint.list_epoch_checkpoints(out)] == [3, 2, 1]
+    # the REFERENCE's resume scan over the same directory (scripts/train_network.py:70-85, restated): every entry it
+    # takes for a weights file must be a model state dict -- the optimizer file must be invisible to it
+    ref_src = "/root/reference/scripts/train_network.py"
+    if os.path.exists(ref_src):                                     # build container only: the rule is still the one restated
+        assert 'x.startswith("epoch") and x.endswith(".pth")' in open(ref_src).read()
+    picked = [x for x in os.listdir(out) if x.startswith("epoch") and x.endswith(".pth")]
+    numbers = [int(x.split("_")[1].split(".")[0]) for x in picked]
+    assert sorted(numbers) == [1, 2, 3]                             # one candidate per epoch: no tie for the newest
+    newest = sorted(zip(picked, numbers), key=lambda pair: pair[1], reverse=True)[0][0]
+    assert newest == "epoch_3.pth"
+    for name in picked:
+        assert all(k.startswith("module.") for k in torch.load(os.path.join(out, name)))
     rp = checkpoint.find_resume_point(out, new_network_config=_config(), total_epochs=5)
     assert rp.start_epoch == 3 and rp.random_seed == 1234
     assert rp.best_valid_loss == pytest.approx(1.0 / 3)
@@ -127,5 +139,5 @@ def test_async_writer_writes_the_same_files(tmp_path):
         sa, sb = torch.load(os.path.join(a_dir, name)), torch.load(os.path.join(b_dir, name))
         assert sa.keys() == sb.keys() and all(torch.equal(sa[k], sb[k]) for k in sa)
     assert network.load_yaml_config(os.path.join(b_dir, "epoch_7.yaml"))["training"]["results"]["epochs_trained"] == 0
-    oa, ob = torch.load(os.path.join(a_dir, "epoch_7.optim.pth")), torch.load(os.path.join(b_dir, "epoch_7.optim.pth"))
+    oa, ob = torch.load(os.path.join(a_dir, "optim_epoch_7.pt")), torch.load(os.path.join(b_dir, "optim_epoch_7.pt"))
     assert all(torch.equal(oa["state"][k]["exp_avg_sq"], ob["state"][k]["exp_avg_sq"]) for k in oa["state"])

@@ -170,3 +170,34 @@ def test_batched_analysis_matches_sample_loop(preproc, raw_res, net_in):
     assert np.array_equal(det, det_ref)                            # same float64 operations, same order
     assert np.array_equal(metric, metric_ref)
     assert metric[5] == 999.999 and metric[7] == 999.999
+
+
+def test_pretrained_trunks_load_from_a_local_checkpoint_or_warn(tmp_path, monkeypatch):
+    """dream/models.py:22,587 build the trunks from torchvision's pretrained nets; here that is a LOCAL file lookup
+    (no download): found -> copied into the reference-named parameters, absent -> a warning, never silence."""
+    import warnings
+    from dream_b200 import models, pretrained
+    monkeypatch.setenv("DREAMB200_PRETRAINED_DIR", str(tmp_path))
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path / "nohub"))
+    pretrained._WARNED.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        models.DreamHourglass(7, internalize_spatial_softmax=False)
+        models.ResnetSimple(7)
+        models.ResnetSimple(7, pretrained=False)
+    msgs = [str(x.message) for x in w]
+    assert sum("vgg19" in m and "RANDOM" in m for m in msgs) == 1
+    assert sum("resnet101" in m and "RANDOM" in m for m in msgs) == 1
+    # a fake torchvision vgg19 checkpoint: every trunk conv except the fresh first one is taken from it
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False)
+    fake = {}
+    for name, p in net.named_parameters():
+        if name.startswith("layer_0_"):
+            idx, leaf = name.split(".")[1], name.split(".")[2]
+            fake["features.%s.%s" % (idx, leaf)] = torch.full_like(p, float(idx) + (0.5 if leaf == "bias" else 0.0))
+    torch.save(fake, tmp_path / "vgg19-dcbb9e9d.pth")
+    net2 = models.DreamHourglass(7, internalize_spatial_softmax=False)
+    sd = net2.state_dict()
+    assert float(sd["layer_0_3_down.12.weight"].mean()) == 12.0 and float(sd["layer_0_5_down.34.bias"].mean()) == 34.5
+    assert float(sd["layer_0_1_down.2.weight"].mean()) == 2.0
+    assert float(sd["layer_0_1_down.0.weight"].abs().max()) < 1.0          # the fresh first conv keeps its own init

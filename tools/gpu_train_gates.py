@@ -93,7 +93,8 @@ def curve_case(res, B, steps, lr, opt_type="sgd", loss_type="mse", mode="he", ga
     net.enable_training()
     gen = torch.Generator().manual_seed(1)
     x = torch.rand((B, 3, res[0], res[1]), generator=gen) * 2 - 1
-    t = torch.rand((B, 7, res[0] // 4, res[1] // 4), generator=gen)
+    out_w, out_h = net.trained_net_output_resolution()
+    t = torch.rand((B, 7, out_h, out_w), generator=gen)
     osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     opt = (torch.optim.SGD if opt_type == "sgd" else torch.optim.Adam)(list(osd.values()), lr=lr)
     crit = torch.nn.MSELoss() if loss_type == "mse" else torch.nn.SmoothL1Loss()
@@ -151,8 +152,8 @@ if __name__ == "__main__":
         print(json.dumps(determ_case()), flush=True)
     if "curve" in which:
         print(json.dumps(curve_case((64, 96), 4, 4, 0.002)), flush=True)
-        print(json.dumps(curve_case((200, 200), 2, 20, 0.002)), flush=True)
-        print(json.dumps(curve_case((200, 200), 2, 20, 1.5e-4, "adam", mode="default", gain=13.0)), flush=True)
+        print(json.dumps(curve_case((192, 192), 2, 20, 0.002)), flush=True)
+        print(json.dumps(curve_case((192, 192), 2, 20, 1.5e-4, "adam", mode="default", gain=13.0)), flush=True)
         print(json.dumps(curve_case((400, 400), 2, 12, 0.002)), flush=True)
     if "huber" in which:
         print(json.dumps(huber_case()), flush=True)
