@@ -311,16 +311,69 @@ def test_resnet_training_matches_oracle(full, built_lib):
         worst = min(worst, c)
         decoder = name.startswith("upsample")
         assert c >= (0.95 if decoder else 0.80), (name, c)
-        # (BatchNorm statistics are summed with atomics, so fp16 ReLU / max-pool decisions near zero differ from run
-        #  to run; on this 2-frame batch the norm of a 64-element trunk gradient then moves by ~+-17 %)
+        # (absolute gates; see the fp16-operand floor below for why they cannot be the vgg ones)
         ratio = float(got.norm() / ref.norm().clamp_min(1e-30))
         ratios.append(ratio)
         assert abs(ratio - 1.0) <= (0.15 if decoder else 0.35), (name, ratio)
     ratios.sort()
     assert abs(ratios[len(ratios) // 2] - 1.0) <= 0.05, ratios[len(ratios) // 2]     # median parameter: within 5 %
     print("resnet full=%s worst gradient cosine %.5f" % (full, worst))
+    # What the gate above can and cannot be: the SAME comparison for the oracle against itself with nothing but its
+    # conv operands rounded to fp16 in the forward pass (exact fp32 backward) -- the reference algorithm seen through
+    # 11-bit operands, which is also what the reference's own TF32 cuDNN path computes.  A He-scaled, randomly
+    # initialised 101-layer BatchNorm network amplifies that rounding chaotically: measured on this fixture the
+    # emulation alone reaches trunk cosines of 0.85 (0.43 on a 4 x 224 x 224 batch), with every BN reduction
+    # deterministic on our side (profiles/r02_train_gates.jsonl).  So the CUDA path is gated on being NO WORSE than
+    # that floor, quantile by quantile; the exactness of each unit's backward is the teacher-forced test below.
+    esd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not ("running" in k) else v.clone())
+           for k, v in sd.items()}
+    with ref_models.fp16_operands():
+        torch.nn.functional.mse_loss(ref_models.resnet_forward(esd, x, full=full, training=True, prefix=""),
+                                     target).backward()
+    ours_c, emu_c = [], []
+    for name, p in params.items():
+        ref = osd[name].grad
+        if name.startswith("upsample") and name.endswith("bias") and name not in (head + ".bias",):
+            continue
+        ours_c.append(_cos(p.grad.cpu(), ref))
+        emu_c.append(_cos(esd[name].grad, ref))
+    ours_c.sort(); emu_c.sort()
+    n = len(ours_c)
+    for q in (0, n // 20, n // 4, n // 2):
+        assert ours_c[q] >= emu_c[q] - 0.05, ("quantile", q, ours_c[q], emu_c[q])
+    print("resnet full=%s cosine quantiles ours %s | fp16-operand oracle %s" % (
+        full, ["%.3f" % ours_c[q] for q in (0, n // 20, n // 4, n // 2)],
+        ["%.3f" % emu_c[q] for q in (0, n // 20, n // 4, n // 2)]))
     head = "upsample2.3" if full else "upsample.12"
     assert _rel(params[head + ".weight"].grad.cpu(), osd[head + ".weight"].grad) <= 1e-2
+
+
+def test_resnet_training_is_deterministic(built_lib):
+    """Two identical training passes: the forward output, every BatchNorm running statistic and every BatchNorm
+    gradient are bit-identical (two-stage fixed-order reductions, no floating-point atomics); the conv weight
+    gradients, which add split-K partial sums with fp32 atomics, agree to summation-order noise."""
+    from dream_b200 import models
+    sd, x, gen, _ = _resnet_setup(False, 3, (2, 3, 160, 160))
+    runs = []
+    for _ in range(2):
+        net = models.ResnetSimple(7, full=False)
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        out = net(x.cuda())[0]
+        out.pow(2).mean().backward()
+        runs.append((out.detach().clone(), {k: v.clone() for k, v in net.named_buffers()},
+                     {k: p.grad.clone() for k, p in net.named_parameters()}))
+    a, b = runs
+    assert torch.equal(a[0], b[0])
+    for k in a[1]:
+        assert torch.equal(a[1][k], b[1][k]), k
+    for k in a[2]:
+        if float(a[2][k].abs().max()) > 0:
+            assert _rel(a[2][k], b[2][k]) <= 2e-3, (k, _rel(a[2][k], b[2][k]))
+    bn_keys = [k for k in a[2] if (".bn" in k or k.startswith("bn1"))]
+    assert len(bn_keys) >= 200
+    same = sum(1 for k in bn_keys if torch.equal(a[2][k], b[2][k]))
+    assert same >= (9 * len(bn_keys)) // 10, (same, len(bn_keys))      # measured: 218 of 221 (profiles/r02_train_gates.jsonl)
 
 
 def resnet_unit_report(full=False, seed=4, shape=(2, 3, 128, 160), every=3):
@@ -420,6 +473,71 @@ def test_training_steps_track_oracle_loss_curve(built_lib):
         ref.backward()
         opt.step()
         assert abs(loss.item() - ref.item()) <= 5e-3 * ref.item(), (step, loss.item(), ref.item())
+
+
+def test_huber_loss_through_the_facade(built_lib):
+    """architecture.loss.type = "huber" (dream/network.py:289-290: SmoothL1Loss): loss value and gradients vs the
+    oracle with the same criterion, targets chosen so that errors fall on both sides of the Huber knee."""
+    from conftest import panda_config
+    from dream_b200 import network
+    cfg = panda_config("vgg")
+    cfg["architecture"]["loss"] = {"type": "huber"}
+    cfg["training"]["config"]["net_input_resolution"] = [96, 64]
+    net = network.create_network_from_config_data(cfg)
+    assert isinstance(net.criterion, torch.nn.SmoothL1Loss)
+    sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=6, out_gain=13.0, mode="default")
+    net.model.load_state_dict(sd)
+    net.enable_training()
+    gen = torch.Generator().manual_seed(2)
+    x = torch.rand((3, 3, 64, 96), generator=gen) * 2 - 1
+    t = torch.rand((3, 7, 16, 24), generator=gen) * 3 - 1
+    net.optimizer.zero_grad()
+    loss = net.loss([x.cuda()], t.cuda())
+    loss.backward()
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y = ref_models.vgg_forward(osd, x)
+    assert float(((y - t).abs() < 1).float().mean()) > 0.1 and float(((y - t).abs() > 1).float().mean()) > 0.1
+    ref = torch.nn.SmoothL1Loss()(y, t)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-3 * ref.item()
+    for name, p in net.model.named_parameters():
+        got, want = p.grad.cpu(), osd[name].grad
+        assert _cos(got, want) >= 0.985, (name, _cos(got, want))
+        assert abs(float(got.norm() / want.norm()) - 1.0) <= 0.03, name
+        if name.startswith("module.heads_0"):
+            assert _rel(got, want) <= 1e-2, (name, _rel(got, want))
+
+
+def test_twenty_training_steps_track_the_oracle_at_192(built_lib):
+    """20 optimizer steps (SGD, then Adam with the shipped learning rate) on a 2 x 192 x 192 batch through
+    DreamNetwork.train against the same steps on the oracle: every step's loss within 5e-3, and the loss must
+    actually move, so that fp16 gradient quality has something to show."""
+    from conftest import panda_config
+    from dream_b200 import network
+    for opt_type, lr, mode, gain in (("sgd", 0.002, "he", 0.1), ("adam", 1.5e-4, "default", 13.0)):
+        cfg = panda_config("vgg")
+        cfg["training"]["config"]["net_input_resolution"] = [192, 192]
+        cfg["training"]["config"]["optimizer"] = {"type": opt_type, "learning_rate": lr}
+        net = network.create_network_from_config_data(cfg)
+        sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7), seed=5, out_gain=gain, mode=mode)
+        net.model.load_state_dict(sd)
+        net.enable_training()
+        gen = torch.Generator().manual_seed(1)
+        x = torch.rand((2, 3, 192, 192), generator=gen) * 2 - 1
+        t = torch.rand((2, 7, 48, 48), generator=gen)
+        osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = (torch.optim.SGD if opt_type == "sgd" else torch.optim.Adam)(list(osd.values()), lr=lr)
+        first = last = None
+        for step in range(20):
+            loss = net.train([x.cuda()], t.cuda())
+            opt.zero_grad()
+            ref = torch.nn.functional.mse_loss(ref_models.vgg_forward(osd, x), t)
+            ref.backward()
+            opt.step()
+            assert abs(loss.item() - ref.item()) <= 5e-3 * ref.item(), (opt_type, step, loss.item(), ref.item())
+            first = ref.item() if first is None else first
+            last = ref.item()
+        assert last < 0.9 * first, (opt_type, first, last)
 
 
 def test_fused_scale_mask_bias_and_epilogue_absmax(built_lib):
