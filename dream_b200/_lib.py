@@ -56,7 +56,7 @@ _PROTOS = {
     "dreamb200_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
-    "dreamb200_peaks_scratch_floats": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_longlong)]),
+    "dreamb200_peaks_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
     "dreamb200_gaussian_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_void_p]),
     "dreamb200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 +

@@ -26,6 +26,8 @@
 // dreamb200_softargmax: SoftArgmaxPavlo.forward (dream/spatial_softmax.py:24-95), one CTA per map.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "dreamb200.h"
 
@@ -251,9 +253,9 @@ __device__ __forceinline__ float d2f_fast(double d, uint32_t& flag) {
 // Reference form of one task (the arithmetic of gauss_pass_kernel: hardware conversions, general reflection): used for
 // flagged tasks and for axes shorter than the register window.
 static __device__ __noinline__ void gauss_task_exact(const float* __restrict__ line, int s_axis,
-                                                     float* __restrict__ out_line, int d_axis, int c0, int n_axis,
-                                                     const GaussW& gw) {
-  for (int j = 0; j < kStrip && c0 + j < n_axis; ++j) {
+                                                     float* __restrict__ out_line, int d_axis, int c0, int c_end,
+                                                     int n_axis, const GaussW& gw) {
+  for (int j = 0; j < kStrip && c0 + j < c_end; ++j) {
     const int c = c0 + j;
     double acc = __dmul_rn((double)line[c * s_axis], gw.w[0]);
     for (int d = kFusedRadius; d >= 1; --d) {
@@ -267,20 +269,25 @@ static __device__ __noinline__ void gauss_task_exact(const float* __restrict__ l
 // One separable pass over a [n_other lines] x [n_axis samples] map.  Element (line o, sample i) of the source is
 // src[o*s_other + i*s_axis]; thread tasks are (strip, line) with the line index fastest, so that consecutive lanes
 // touch consecutive lines (the caller picks layouts where that is conflict free).  Arithmetic = gauss_pass_kernel's.
-// Out of line: both passes share one copy of the unrolled body (instruction cache).
+// Outputs are produced for the axis positions [out_begin, out_begin + out_count) and stored at dst index
+// (position - out_begin); the whole-map kernel asks for all of them, a band only for its rows (its halo rows are part
+// of the source, so nothing is reflected there).  Out of line: both passes share one copy of the unrolled body.
 static __device__ __noinline__ void gauss_strips(const float* __restrict__ src, int s_axis, int s_other,
                                                  float* __restrict__ dst, int d_axis, int d_other, int n_axis,
-                                                 int n_other, const GaussW& gw) {
-  const int strips = (n_axis + kStrip - 1) / kStrip;
+                                                 int n_other, int out_begin, int out_count, const GaussW& gw) {
+  const int strips = (out_count + kStrip - 1) / kStrip;
   const int tasks = strips * n_other;
+  const int out_end = out_begin + out_count;
   const uint32_t magic = 0xffffffffu / (uint32_t)n_other + 1u;      // t / n_other == umulhi(t, magic) for t*n_other < 2^32
-  const bool windowed = n_axis >= kStrip + 2 * kFusedRadius;        // one reflection per side is enough
+  // the register window reflects an index at most once per side: enough when every index it can touch, -12 on the
+  // left and (last output position + 9 + 12) on the right, lands inside [0, n_axis) after one reflection
+  const bool windowed = n_axis > kFusedRadius && 2 * n_axis - 1 >= out_end + kStrip - 1 + kFusedRadius;
   for (int t = threadIdx.x; t < tasks; t += kFusedThreads) {
     const int strip = (int)__umulhi((uint32_t)t, magic);
     const int o = t - strip * n_other;
-    const int c0 = strip * kStrip;
+    const int c0 = out_begin + strip * kStrip;
     const float* line = src + o * s_other;
-    float* out_line = dst + o * d_other;
+    float* out_line = dst + o * d_other - out_begin * d_axis;       // indexed by the axis position
     uint32_t flag = windowed ? 0u : 1u;
     if (windowed) {
       double v[kStrip + 2 * kFusedRadius];
@@ -298,10 +305,10 @@ static __device__ __noinline__ void gauss_strips(const float* __restrict__ src, 
         for (int d = kFusedRadius; d >= 1; --d)
           acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[j + kFusedRadius - d], v[j + kFusedRadius + d]), gw.w[d]));
         const float r = d2f_fast(acc, flag);
-        if (c0 + j < n_axis) out_line[(c0 + j) * d_axis] = r;
+        if (c0 + j < out_end) out_line[(c0 + j) * d_axis] = r;
       }
     }
-    if (flag != 0u) gauss_task_exact(line, s_axis, out_line, d_axis, c0, n_axis, gw);
+    if (flag != 0u) gauss_task_exact(line, s_axis, out_line, d_axis, c0, out_end, n_axis, gw);
   }
 }
 
@@ -388,10 +395,10 @@ peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, con
     }
     __syncthreads();
     // ---- axis 0 (along y): lines = columns x; reads bufA[y*w + x], writes bufB[x*hp + y]
-    gauss_strips(bufA, w, 1, bufB, 1, hp, h, w, gw);
+    gauss_strips(bufA, w, 1, bufB, 1, hp, h, w, 0, h, gw);
     __syncthreads();
     // ---- axis 1 (along x): lines = rows y; reads bufB[x*hp + y], writes bufA[x*hp + y]
-    gauss_strips(bufB, hp, 1, bufA, hp, 1, w, h, gw);
+    gauss_strips(bufB, hp, 1, bufA, hp, 1, w, h, 0, w, gw);
     __syncthreads();
     // ---- peak test -> bitmask in raster order
     const float* sm = bufA;
@@ -484,6 +491,233 @@ peaks_fused_kernel(const float* __restrict__ maps, int n_maps, int h, int w, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// banded path: maps too large for one CTA's shared memory (resnet-H 208x208, full-resolution decoders 400x400 /
+// 480x640) are cut into bands of `hb` rows; a CTA owns (map, band).
+// ---------------------------------------------------------------------------------------------
+// It stages the band's rows plus a halo of 13 rows above and below (reflected at the image border exactly like
+// scipy's line extension), filters rows y0-1 .. y1 along y and then along x in shared memory (the extra row on
+// either side is what the 4-neighbour test of the band's first / last row looks at), runs the same peak test /
+// ordered compaction / centroids as the whole-map kernel on its rows and leaves its peaks in a staging record.
+// The CTA that draws the LAST ticket of a map concatenates the bands' records in band order (= raster order)
+// into the peak table and merges their best / runner-up summaries.  One launch, fixed order, no sorting.
+struct BandHeader {
+  int count;        // peaks found in the band (may exceed the staged capacity)
+  int pad;
+  Top2 top;         // best / runner-up of the band (raster index i0 is the global one)
+};
+struct BandPeak {
+  double x, y;
+  float score;
+  int px, py;
+  int pad;
+};
+struct BandParams {
+  int n_maps, h, w, hb, n_bands, cap;
+  double offset;
+  unsigned char* stage;      // [n_maps][n_bands] records of (BandHeader + cap * BandPeak)
+  unsigned* tickets;         // [n_maps], zero on entry
+  double* peak_xy;
+  float* peak_score;
+  int32_t* peak_ij;
+  int32_t* counts;
+  double* summary;
+};
+
+__global__ void __launch_bounds__(kFusedThreads, 2)
+peaks_banded_kernel(const float* __restrict__ maps, const __grid_constant__ GaussW gw,
+                    const __grid_constant__ BandParams P) {
+  extern __shared__ __align__(16) float fsm[];
+  const int h = P.h, w = P.w;
+  const int map = blockIdx.x / P.n_bands, band = blockIdx.x - map * P.n_bands;
+  const int y0 = band * P.hb;
+  const int rows = min(P.hb, h - y0);
+  const int rows_in = rows + 2 * kFusedRadius + 2;            // global rows y0-13 .. y0+rows+12
+  const int rows_out = rows + 2;                              // smoothed rows y0-1 .. y0+rows
+  const int hp = rows_out | 1;
+  float* bufA = fsm;                                          // [rows_in][w]; later the smoothed rows, transposed [w][hp]
+  float* bufB = fsm + max(rows_in * w, w * hp);               // axis-0 result, transposed [w][hp]
+  __shared__ uint32_t mask[kMaxMaskWords];
+  __shared__ int pref[kMaxMaskWords];
+  __shared__ Top2 warp_top[kFusedThreads / 32];
+  __shared__ int total_s;
+  __shared__ bool last_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* mo = maps + (long long)map * h * w;
+  // ---- rows (reflected at the image border) -> shared
+  for (int r = wid; r < rows_in; r += kFusedThreads / 32) {
+    const int gy = reflect_idx(y0 - kFusedRadius - 1 + r, h);
+    const float* srow = mo + (long long)gy * w;
+    for (int x = lane; x < w; x += 32) bufA[r * w + x] = __ldg(srow + x);
+  }
+  __syncthreads();
+  // ---- axis 0: output row l (global y0-1+l) is centred on staged row l+13
+  gauss_strips(bufA, w, 1, bufB, 1, hp, rows_in, w, kFusedRadius + 1, rows_out, gw);
+  __syncthreads();
+  // ---- axis 1: full rows, reflected at x = 0 / w like the whole-map kernel
+  gauss_strips(bufB, hp, 1, bufA, hp, 1, w, rows_out, 0, w, gw);
+  __syncthreads();
+  // ---- peak test on the band's rows (local row l = 1 .. rows), bitmask in raster order
+  const float* sm = bufA;
+  const int total = rows * w;
+  const int words = (total + 31) >> 5;
+  const uint32_t wmagic = 0xffffffffu / (uint32_t)w + 1u;
+  for (int base = wid * 32; base < words * 32; base += kFusedThreads) {
+    const int idx = base + lane;
+    bool is_peak = false;
+    if (idx < total) {
+      const int ly = (int)__umulhi((uint32_t)idx, wmagic), px = idx - ly * w;
+      const int py = y0 + ly;
+      const float* c = sm + px * hp + ly + 1;
+      const float v = c[0];
+      const float up = py > 0 ? c[-1] : 0.0f;
+      const float dn = py < h - 1 ? c[1] : 0.0f;
+      const float lf = px > 0 ? c[-hp] : 0.0f;
+      const float rt = px < w - 1 ? c[hp] : 0.0f;
+      is_peak = (v >= up) && (v >= dn) && (v >= lf) && (v >= rt) && (v > 0.01f);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_peak);
+    if (lane == 0) mask[base >> 5] = ballot;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    int running = 0;
+    for (int b = 0; b < words; b += 32) {
+      const int c = b + lane < words ? __popc(mask[b + lane]) : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (b + lane < words) pref[b + lane] = running + inc - c;
+      running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) total_s = running;
+  }
+  __syncthreads();
+  const size_t rec_bytes = sizeof(BandHeader) + (size_t)P.cap * sizeof(BandPeak);
+  unsigned char* rec = P.stage + ((size_t)map * P.n_bands + band) * rec_bytes;
+  BandPeak* staged = reinterpret_cast<BandPeak*>(rec + sizeof(BandHeader));
+  Top2 mine;
+  mine.n = 0; mine.i0 = -1; mine.s0 = 0.f; mine.s1 = 0.f; mine.x0 = 0.0; mine.y0 = 0.0;
+  for (int wd = tid; wd < words; wd += kFusedThreads) {
+    uint32_t bits = mask[wd];
+    int slot = pref[wd];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int idx = wd * 32 + b;
+      const int ly = (int)__umulhi((uint32_t)idx, wmagic), px = idx - ly * w;
+      const int py = y0 + ly;
+      double cx, cy;
+      peak_centroid(mo, h, w, px, py, P.offset, &cx, &cy);
+      const float score = __ldg(mo + py * w + px);
+      if (slot < P.cap) {
+        BandPeak bp;
+        bp.x = cx; bp.y = cy; bp.score = score; bp.px = px; bp.py = py; bp.pad = 0;
+        staged[slot] = bp;
+      }
+      ++slot;
+      top2_insert(mine, score, py * w + px, cx, cy);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const Top2 o = top2_shfl_xor(mine, m);
+    top2_merge(mine, o);
+  }
+  if (lane == 0) warp_top[wid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    Top2 t = warp_top[0];
+    for (int i = 1; i < kFusedThreads / 32; ++i) top2_merge(t, warp_top[i]);
+    BandHeader* hd = reinterpret_cast<BandHeader*>(rec);
+    hd->count = total_s;
+    hd->pad = 0;
+    hd->top = t;
+  }
+  // ---- the last band of the map to finish assembles the map's rows of the peak table
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = atomicAdd(P.tickets + map, 1u) == (unsigned)P.n_bands - 1u;
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  const unsigned char* recs = P.stage + (size_t)map * P.n_bands * rec_bytes;
+  if (wid == 0) {
+    // exclusive prefix of the band counts into pref[] (n_bands <= kMaxMaskWords), total into total_s
+    int running = 0;
+    for (int b = 0; b < P.n_bands; b += 32) {
+      int c = 0;
+      if (b + lane < P.n_bands) c = __ldcg(&reinterpret_cast<const BandHeader*>(recs + (size_t)(b + lane) * rec_bytes)->count);
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (b + lane < P.n_bands) pref[b + lane] = running + inc - c;
+      running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) total_s = running;
+  }
+  __syncthreads();
+  for (int b = wid; b < P.n_bands; b += kFusedThreads / 32) {
+    const unsigned char* r = recs + (size_t)b * rec_bytes;
+    const int cnt = min(__ldcg(&reinterpret_cast<const BandHeader*>(r)->count), P.cap);
+    const BandPeak* sp = reinterpret_cast<const BandPeak*>(r + sizeof(BandHeader));
+    for (int i = lane; i < cnt; i += 32) {
+      const int slot = pref[b] + i;
+      if (slot >= P.cap) break;
+      const size_t o = (size_t)map * P.cap + slot;
+      const double x = __ldcg(&sp[i].x), y = __ldcg(&sp[i].y);
+      P.peak_xy[2 * o] = x;
+      P.peak_xy[2 * o + 1] = y;
+      P.peak_score[o] = __ldcg(&sp[i].score);
+      P.peak_ij[2 * o] = __ldcg(&sp[i].px);
+      P.peak_ij[2 * o + 1] = __ldcg(&sp[i].py);
+    }
+  }
+  if (tid == 0) {
+    Top2 t;
+    t.n = 0; t.i0 = -1; t.s0 = 0.f; t.s1 = 0.f; t.x0 = 0.0; t.y0 = 0.0;
+    for (int b = 0; b < P.n_bands; ++b) {
+      const BandHeader* hd = reinterpret_cast<const BandHeader*>(recs + (size_t)b * rec_bytes);
+      Top2 o;
+      o.s0 = __ldcg(&hd->top.s0); o.s1 = __ldcg(&hd->top.s1); o.i0 = __ldcg(&hd->top.i0); o.n = __ldcg(&hd->top.n);
+      o.x0 = __ldcg(&hd->top.x0); o.y0 = __ldcg(&hd->top.y0);
+      top2_merge(t, o);
+    }
+    P.counts[map] = total_s;
+    P.summary[4 * map + 0] = t.x0;
+    P.summary[4 * map + 1] = t.y0;
+    P.summary[4 * map + 2] = (double)t.s0;
+    P.summary[4 * map + 3] = (double)t.s1;
+  }
+}
+
+// band height for a map of h x w: as tall as ~100 KB of shared memory allows (two CTAs per SM), but short enough that
+// the launch has at least two CTAs per SM when the batch is small; 0 = the map is too wide for the banded kernel
+static int band_rows(int n_maps, int h, int w, size_t* smem_out) {
+  auto smem = [&](int hb) {
+    const int rows_in = hb + 2 * kFusedRadius + 2, hp = (hb + 2) | 1;
+    return (size_t)(std::max(rows_in * w, w * hp) + w * hp) * sizeof(float);
+  };
+  int hb = 0;
+  for (int c = 1; c <= h && c <= 96; ++c)
+    if (smem(c) <= 100 * 1024 && (long long)c * w <= 32LL * kMaxMaskWords) hb = c;
+  if (hb == 0) return 0;
+  const int want_ctas = 2 * device_sm_count();
+  while (hb >= 16 && (long long)n_maps * ((h + hb - 1) / hb) < want_ctas) hb = (hb + 1) / 2;
+  if ((h + hb - 1) / hb > kMaxMaskWords) return 0;
+  *smem_out = smem(hb);
+  return hb;
+}
+static size_t band_stage_bytes(int n_maps, int n_bands, int cap) {
+  return (size_t)n_maps * n_bands * (sizeof(BandHeader) + (size_t)cap * sizeof(BandPeak)) + (size_t)n_maps * 4 + 64;
+}
+
 static size_t fused_smem_bytes(int h, int w) { return (size_t)2 * w * (h | 1) * sizeof(float); }
 static int fused_set_smem(size_t smem) {
   static size_t smem_set = 0;
@@ -564,6 +798,17 @@ softargmax_kernel(const float* __restrict__ maps, const float* __restrict__ beta
   }
 }
 
+// 0 = whole map per CTA (peaks_fused_kernel), 1 = bands (peaks_banded_kernel), 2 = the three generic kernels.
+// DREAMB200_PEAKS_UNFUSED forces 2, DREAMB200_PEAKS_BANDED prefers 1 even where 0 would fit (tests).
+static int peaks_mode(int n_maps, int h, int w, int radius, int* hb, size_t* band_smem) {
+  if (getenv("DREAMB200_PEAKS_UNFUSED") || radius != kFusedRadius) return 2;
+  const bool want_banded = getenv("DREAMB200_PEAKS_BANDED") != nullptr;
+  if (fused_ok(h, w, radius) && !want_banded) return 0;
+  *hb = band_rows(n_maps, h, w, band_smem);
+  if (*hb > 0) return 1;
+  return fused_ok(h, w, radius) ? 0 : 2;
+}
+
 }  // namespace db200
 
 using namespace db200;
@@ -580,11 +825,35 @@ extern "C" int dreamb200_peaks(const float* maps, int n_maps, int h, int w, cons
   DB_REQUIRE((long long)h * w < (1ll << 30), "peaks: map too large");
   GaussW gw;
   for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
-  if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) {
+  size_t band_smem = 0;
+  int hb = 0;
+  const int mode = peaks_mode(n_maps, h, w, radius, &hb, &band_smem);
+  if (mode == 0) {
     const size_t smem = fused_smem_bytes(h, w);
     if (fused_set_smem(smem)) return -2;
     peaks_fused_kernel<<<n_maps, kFusedThreads, smem, stream>>>(maps, n_maps, h, w, gw, offset, cap, peak_xy,
                                                                  peak_score, peak_ij, counts, summary, nullptr);
+    DB_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
+  if (mode == 1) {
+    DB_REQUIRE(scratch, "peaks: the banded kernel needs the scratch buffer (dreamb200_peaks_plan)");
+    DB_REQUIRE(((uintptr_t)scratch & 7) == 0, "peaks: scratch must be 8-byte aligned");
+    BandParams P;
+    P.n_maps = n_maps; P.h = h; P.w = w; P.hb = hb; P.n_bands = (h + hb - 1) / hb; P.cap = cap; P.offset = offset;
+    const size_t rec_bytes = sizeof(BandHeader) + (size_t)cap * sizeof(BandPeak);
+    P.stage = reinterpret_cast<unsigned char*>(scratch);
+    P.tickets = reinterpret_cast<unsigned*>(P.stage + (size_t)n_maps * P.n_bands * rec_bytes);
+    P.peak_xy = peak_xy; P.peak_score = peak_score; P.peak_ij = peak_ij; P.counts = counts; P.summary = summary;
+    static size_t band_smem_set = 0;
+    if (band_smem > band_smem_set) {
+      DB_CHECK_CUDA(cudaFuncSetAttribute(peaks_banded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)band_smem));
+      band_smem_set = band_smem;
+    }
+    DB_CHECK_CUDA(cudaMemsetAsync(P.tickets, 0, (size_t)n_maps * sizeof(unsigned), stream));
+    peaks_banded_kernel<<<n_maps * P.n_bands, kFusedThreads, band_smem, stream>>>(maps, gw, P);
     DB_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -612,7 +881,7 @@ extern "C" int dreamb200_gaussian_smooth(const float* maps, int n_maps, int h, i
   DB_REQUIRE(radius >= 0 && radius <= kMaxRadius, "gaussian_smooth: radius %d out of range", radius);
   GaussW gw;
   for (int i = 0; i <= kMaxRadius; ++i) gw.w[i] = i <= radius ? gauss_w[i] : 0.0;
-  if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) {
+  if (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED") && !getenv("DREAMB200_PEAKS_BANDED")) {
     const size_t smem = fused_smem_bytes(h, w);
     if (fused_set_smem(smem)) return -2;
     peaks_fused_kernel<<<n_maps, kFusedThreads, smem, stream>>>(maps, n_maps, h, w, gw, 0.0, 1, nullptr, nullptr,
@@ -630,9 +899,16 @@ extern "C" int dreamb200_gaussian_smooth(const float* maps, int n_maps, int h, i
   return 0;
 }
 
-extern "C" int dreamb200_peaks_scratch_floats(int n_maps, int h, int w, int radius, long long* n_floats) {
-  DB_REQUIRE(n_floats, "peaks_scratch_floats: null pointer");
-  *n_floats = (fused_ok(h, w, radius) && !getenv("DREAMB200_PEAKS_UNFUSED")) ? 0 : 2LL * n_maps * h * w;
+extern "C" int dreamb200_peaks_plan(int n_maps, int h, int w, int radius, int cap, long long* scratch_floats,
+                                    int* mode_out) {
+  DB_REQUIRE(scratch_floats && mode_out && n_maps > 0 && h > 0 && w > 0 && cap >= 1, "peaks_plan: bad arguments");
+  size_t band_smem = 0;
+  int hb = 0;
+  const int mode = peaks_mode(n_maps, h, w, radius, &hb, &band_smem);
+  *mode_out = mode;
+  if (mode == 0) *scratch_floats = 0;
+  else if (mode == 1) *scratch_floats = (long long)((band_stage_bytes(n_maps, (h + hb - 1) / hb, cap) + 3) / 4);
+  else *scratch_floats = 2LL * n_maps * h * w;
   return 0;
 }
 

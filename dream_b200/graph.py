@@ -54,5 +54,5 @@ def graph_key(network, x):
     """Everything a captured step depends on besides the input VALUES."""
     model = network.model.module
     ver = tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers()))
-    return (tuple(x.shape), x.dtype, x.device.index, model.training, network.use_belief_peak_scores,
+    return (tuple(x.shape), x.dtype, model.training, network.use_belief_peak_scores,
             float(network.belief_peak_next_best_score), hash(ver))

@@ -6,6 +6,7 @@ dreamb200_peaks; the resolution / keypoint-frame helpers the `DreamNetwork` faca
 argument meaning ((width, height) tuples) and assertions.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -49,8 +50,8 @@ def find_peaks_device(maps, offset_due_to_upsampling, cap=64):
     n_maps = maps.numel() // (h * w)
     wts, radius = gaussian_half_kernel()
     table = PeakTable(n_maps, cap, maps.device)
-    need = C.c_longlong(0)
-    check(lib().dreamb200_peaks_scratch_floats(n_maps, h, w, radius, C.byref(need)), "dreamb200_peaks_scratch_floats")
+    need, mode = C.c_longlong(0), C.c_int(0)
+    check(lib().dreamb200_peaks_plan(n_maps, h, w, radius, cap, C.byref(need), C.byref(mode)), "dreamb200_peaks_plan")
     scratch = torch.empty((need.value,), dtype=torch.float32, device=maps.device) if need.value else None
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     check(lib().dreamb200_peaks(C.c_void_p(maps.data_ptr()), n_maps, h, w,
@@ -70,9 +71,11 @@ def gaussian_smooth_device(maps, sigma=_SIGMA):
     h, w = int(maps.shape[-2]), int(maps.shape[-1])
     n_maps = maps.numel() // (h * w)
     wts, radius = gaussian_half_kernel(sigma)
-    need = C.c_longlong(0)
-    check(lib().dreamb200_peaks_scratch_floats(n_maps, h, w, radius, C.byref(need)), "dreamb200_peaks_scratch_floats")
-    scratch = torch.empty((need.value // 2,), dtype=torch.float32, device=maps.device) if need.value else None
+    need, mode = C.c_longlong(0), C.c_int(0)
+    check(lib().dreamb200_peaks_plan(n_maps, h, w, radius, 1, C.byref(need), C.byref(mode)), "dreamb200_peaks_plan")
+    # the smoothing-only entry runs the whole-map kernel (mode 0) or the two generic passes (scratch n_maps*h*w)
+    scratch = None if (mode.value == 0 and not os.environ.get("DREAMB200_PEAKS_BANDED")) else \
+        torch.empty((n_maps * h * w,), dtype=torch.float32, device=maps.device)
     out = torch.empty_like(maps)
     check(lib().dreamb200_gaussian_smooth(C.c_void_p(maps.data_ptr()), n_maps, h, w, wts.ctypes.data_as(C.c_void_p),
                                           radius, C.c_void_p(scratch.data_ptr() if scratch is not None else 0),

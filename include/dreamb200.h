@@ -119,17 +119,20 @@ int dreamb200_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int H, int W,
 
 /* peaks_from_belief_maps for n_maps = B*K maps of h x w fp32 (contiguous).
    gauss_w: 13 fp64 taps w[0..12] for |offset| 0..12 (host computes them like scipy).
-   scratch: dreamb200_peaks_scratch_floats() floats -- 0 (pass NULL) when the map fits the fused one-launch kernel
-   (radius 12 and 2*w*(h|1)*4 bytes of shared memory <= 200 KB), else 2*n_maps*h*w.  peak table: capacity `cap` per map, rows
+   Three implementations, chosen by dreamb200_peaks_plan (same results bit for bit): mode 0 = one CTA per map, the
+   whole map in shared memory (radius 12, maps up to ~160x160); mode 1 = one CTA per band of rows, the last band of a
+   map to finish assembles the table (larger maps: 208x208, 400x400, 480x640); mode 2 = three generic kernels.
+   scratch: `scratch_floats` floats as reported by dreamb200_peaks_plan for the same (n_maps, h, w, radius, cap), 8-byte
+   aligned, contents irrelevant; NULL when 0.  peak table: capacity `cap` per map, rows
    (x:f64, y:f64, score:f32, pad) ; counts[n_maps] = true count (may exceed cap).
    summary[n_maps*4] doubles: best x, best y, best score, second score. */
 int dreamb200_peaks(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
                     double offset, float* scratch, int cap, double* peak_xy, float* peak_score,
                     int32_t* peak_ij, int32_t* counts, double* summary, void* stream);
-int dreamb200_peaks_scratch_floats(int n_maps, int h, int w, int radius, long long* n_floats);
+int dreamb200_peaks_plan(int n_maps, int h, int w, int radius, int cap, long long* scratch_floats, int* mode);
 /* The smoothing stage of dreamb200_peaks alone: out[n_maps,h,w] = scipy.ndimage.gaussian_filter(map, sigma) bit for
    bit (dream/image_proc.py:935; fp64 accumulation in scipy's tap order, "reflect" borders, one rounding to fp32 per
-   pass).  Same kernels as dreamb200_peaks; scratch (n_maps*h*w floats) only when the fused kernel does not apply. */
+   pass).  Same kernels as dreamb200_peaks; scratch (n_maps*h*w floats) unless dreamb200_peaks_plan reports mode 0. */
 int dreamb200_gaussian_smooth(const float* maps, int n_maps, int h, int w, const double* gauss_w, int radius,
                               float* scratch, float* out, void* stream);
 

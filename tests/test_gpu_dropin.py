@@ -116,6 +116,7 @@ def test_training_script_call_sequence_and_resume(dream_overlay, tmp_path, built
     for (ka, a), (kb, b) in zip(net.model.state_dict().items(), fresh.model.state_dict().items()):
         assert ka == kb and torch.equal(a, b)
     x, t = data[0]
+    net.enable_training()                                         # (the epoch loop left it in evaluation mode)
     la, lb = net.train([x.cuda()], t.cuda()).item(), fresh.train([x.cuda()], t.cuda()).item()
     assert abs(la - lb) <= 1e-6 * abs(la)                         # same weights AND same Adam moments: same step
     for a, b in zip(net.model.parameters(), fresh.model.parameters()):

@@ -55,7 +55,7 @@ def _maps(rng, n, h, w, kind):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("h,w,kind", [(100, 100, "blobs"), (100, 100, "noise"), (37, 53, "blobs"), (5, 7, "noise"),
+@pytest.mark.parametrize("h,w,kind", [(100, 100, "blobs"), (100, 100, "noise"), (37, 53, "blobs"), (25, 30, "noise"), (5, 7, "noise"),
                                       (1, 9, "noise"), (120, 160, "blobs"), (64, 48, "plateau"), (13, 11, "plateau")])
 def test_fused_peaks_equal_three_kernel_path_and_oracle(h, w, kind, built_lib):
     from dream_b200 import image_proc
@@ -81,6 +81,40 @@ def test_fused_peaks_equal_three_kernel_path_and_oracle(h, w, kind, built_lib):
         assert fused["counts"][i] == len(xs), i
         c = min(len(xs), 32)
         assert np.array_equal(fused["ij"][i, :c, 0], xs[:c]) and np.array_equal(fused["ij"][i, :c, 1], ys[:c]), i
+
+
+@pytest.mark.parametrize("h,w,n,kind", [(100, 100, 21, "blobs"), (37, 53, 5, "noise"), (208, 208, 14, "blobs"),
+                                        (400, 400, 7, "blobs"), (480, 640, 7, "blobs"), (208, 208, 3, "noise"),
+                                        (300, 40, 4, "plateau"), (26, 700, 2, "noise")])
+def test_banded_peaks_equal_the_other_paths_and_oracle(h, w, n, kind, built_lib):
+    """peaks_banded_kernel (one CTA per band of rows; resnet-H 208x208 and the full-resolution decoders' maps) against
+    the three generic kernels -- and the whole-map kernel where the map fits -- on the same maps: identical tables,
+    counts and summaries; integer peak set equal to scipy's (oracle) on a sample.  Small batches make the bands short
+    (more CTAs than SMs), so band seams cross peaks, plateaus and the reflected image border."""
+    from dream_b200 import image_proc
+    rng = np.random.default_rng(h * 7 + w)
+    maps = _maps(rng, n, h, w, kind)
+    dev = torch.from_numpy(maps).cuda()
+    cap = 48
+    with env(DREAMB200_PEAKS_BANDED="1", DREAMB200_PEAKS_UNFUSED=None):
+        banded = _table_np(image_proc.find_peaks_device(dev, 0.4395, cap=cap))
+    with env(DREAMB200_PEAKS_BANDED=None, DREAMB200_PEAKS_UNFUSED="1"):
+        three = _table_np(image_proc.find_peaks_device(dev, 0.4395, cap=cap))
+    with env(DREAMB200_PEAKS_BANDED=None, DREAMB200_PEAKS_UNFUSED=None):
+        default = _table_np(image_proc.find_peaks_device(dev, 0.4395, cap=cap))
+    for other in (three, default):
+        assert np.array_equal(banded["counts"], other["counts"])
+        for i in range(n):
+            c = min(int(banded["counts"][i]), cap)
+            for k in ("xy", "score", "ij"):
+                assert np.array_equal(banded[k][i, :c], other[k][i, :c]), (i, k)
+            if banded["counts"][i] > 0:
+                assert np.array_equal(banded["summary"][i], other["summary"][i]), i
+    for i in range(min(n, 3)):
+        ys, xs = np.nonzero(ref_peaks.peak_mask(ref_peaks.gaussian_filter_f32(maps[i])))
+        assert banded["counts"][i] == len(xs), i
+        c = min(len(xs), cap)
+        assert np.array_equal(banded["ij"][i, :c, 0], xs[:c]) and np.array_equal(banded["ij"][i, :c, 1], ys[:c]), i
 
 
 @pytest.mark.parametrize("h,w", [(100, 100), (37, 53), (7, 5), (120, 160)])
@@ -258,3 +292,24 @@ def test_cuda_graph_inference_is_bit_identical_to_eager_and_follows_the_weights(
     net.use_cuda_graphs = False
     rb = net.keypoints_from_image(img)
     assert np.array_equal(ra["detected_keypoints"], rb["detected_keypoints"])
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_resnet_l2_blocked_stages_are_bit_identical_to_whole_batch(full, built_lib):
+    """ResnetSimple.belief_maps runs the bottleneck stages on batch chunks sized for the L2 (models.py); every image
+    is computed by the same tiles either way, so the belief maps must not change by a bit -- whatever the chunk size."""
+    from dream_b200 import models
+    from oracle import ref_models
+    sd = ref_models.synth_state_dict(ref_models.resnet_state_shapes(7, full=full, prefix=""), seed=2, out_gain=0.05,
+                                     mode="he")
+    net = models.ResnetSimple(7, full=full, pretrained=False)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x = (torch.rand((5, 3, 96, 128), generator=torch.Generator().manual_seed(0)) * 2 - 1).cuda()
+    outs = []
+    with torch.no_grad():
+        for mb in (0, 40e6, 0.3e6, 0.05e6):          # off, default, chunks of a few images, chunks of one image
+            net.l2_block_bytes = int(mb)
+            outs.append(net.belief_maps(x).clone())
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)

@@ -315,16 +315,19 @@ def test_prefetching_pipeline_matches_direct_inference(built_lib):
     net.model.load_state_dict(sd)
     net.enable_evaluation()
     gen = torch.Generator().manual_seed(2)
-    batches = [(torch.rand((3, 3, 64, 96), generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
+    batches = [(torch.rand((n, 3, 64, 96), generator=gen) * 2 - 1).pin_memory() for n in (3, 3, 3, 3, 2)]   # ragged end
     direct = []
     with torch.no_grad():
         for x in batches:
             b, k = net.inference(x.cuda())
             direct.append((b.cpu(), k))
-    streamed = [(b.cpu(), k) for b, k in pipeline.inference_stream(net, batches)]
-    assert len(streamed) == 4
-    for (b0, k0), (b1, k1) in zip(direct, streamed):
-        assert torch.equal(b0, b1) and torch.equal(k0, k1)
+    for graphs in (True, False, True):               # CUDA-graph pairs (captured, then reused) and eager launches
+        net.use_cuda_graphs = graphs
+        streamed = [(b.cpu(), k) for b, k in pipeline.inference_stream(net, batches)]
+        assert len(streamed) == 5
+        for (b0, k0), (b1, k1) in zip(direct, streamed):
+            assert torch.equal(b0, b1) and torch.equal(k0, k1)
+    assert len(net._stream_graphs) == 2              # one pair per batch shape, captured once
 
 
 def test_facade_single_image_and_checkpoint_round_trip(tmp_path, built_lib):
