@@ -43,6 +43,7 @@ _PROTOS = {
     "dreamb200_launch_count": (C.c_int64, []),
     "dreamb200_conv_tile_utilization": (C.c_double, [C.c_int] * 4),
     "dreamb200_conv2d_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "dreamb200_conv2d_fwd_phases": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "dreamb200_first_conv3x3": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "dreamb200_first_conv3x3_u8": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p]),
     "dreamb200_normalize_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 3),

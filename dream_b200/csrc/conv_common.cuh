@@ -31,6 +31,10 @@ struct ConvParams {
   const __half* gate;      // optional ReLU gate of the backward pass: output zeroed where gate <= 0
   const float* out_scale;  // optional device scalar multiplied into every output
   float* colsum;           // optional [Cout_pad]: += sum over output pixels (after gate / scale): a bias gradient
+  // phase groups (conv_tc2.cu): `phases` sub-pixel convolutions in one launch, tile index = phase * tiles_per_phase + q;
+  // the tap tables above then hold phases * taps entries, phase-major.  0 / 1 = an ordinary convolution.
+  int phases, tiles_per_phase;
+  unsigned long long mg_phase;
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }

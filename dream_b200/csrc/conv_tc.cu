@@ -289,7 +289,8 @@ double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, i
 }
 
 int device_sm_count();
-int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_tc2.cu (opt-in)
+int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_tc2.cu
+int try_conv_tc2_phases(const dreamb200_conv_desc* descs, int n_phases, cudaStream_t stream);
 int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream);   // conv_rs.cu
 int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_rs2.cu
 
@@ -444,7 +445,7 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
   DB_REQUIRE((d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0,
              "conv: output strides must be multiples of 16 bytes");
   {
-    int r = try_conv_tc2(d, stream);           // CTA-pair kernel for the wide layers (opt-in: DREAMB200_TC2=1)
+    int r = try_conv_tc2(d, stream);           // CTA-pair kernel for the wide layers (DREAMB200_TC2=0 switches it off)
     if (r != 0) return r > 0 ? 0 : r;
     r = try_conv_rs2(d, stream);               // CTA-pair slab kernel (DREAMB200_RS2 bit mask)
     if (r != 0) return r > 0 ? 0 : r;
@@ -454,4 +455,28 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
   if (d->Cout_pad % 256 == 0) return launch<256, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
   if (d->Cout_pad % 128 == 0) return launch<128, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
   return launch<64, DREAMB200_OUT_NHWC_F16>(d, stream, sms);
+}
+
+extern "C" int dreamb200_conv2d_fwd_phases(const dreamb200_conv_desc* descs, int n_phases, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  DB_REQUIRE(descs != nullptr && n_phases >= 1 && n_phases <= 4, "conv phases: bad arguments (n_phases=%d)", n_phases);
+  if (n_phases > 1) {
+    bool ok = true;
+    for (int ph = 0; ph < n_phases && ok; ++ph) {
+      const dreamb200_conv_desc* d = descs + ph;
+      ok = d->x && d->w && d->y && d->Cin > 0 && d->Cin % 64 == 0 && d->taps >= 1 && d->Cout_pad % 64 == 0 &&
+           ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0 &&
+           (d->y_stride_w * 2) % 16 == 0 && (d->y_stride_h * 2) % 16 == 0 && (d->y_stride_b * 2) % 16 == 0 &&
+           (d->in_stride == 1 || d->in_stride == 2) && d->B > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0;
+    }
+    if (ok) {
+      const int r = try_conv_tc2_phases(descs, n_phases, stream);
+      if (r != 0) return r > 0 ? 0 : r;
+    }
+  }
+  for (int ph = 0; ph < n_phases; ++ph) {          // not a group the pair kernel takes: one launch per phase
+    const int rc = dreamb200_conv2d_fwd(descs + ph, stream_v);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }

@@ -1,6 +1,13 @@
 // conv_tc2.cu -- CTA-pair (tcgen05 cta_group::2) variant of the generic tap-sum convolution (conv_tc.cu) for the wide
-// layers (Cout % 256 == 0).  OPT-IN (DREAMB200_TC2=1) and NOT YET VALIDATED ON A GPU: written at the end of round 1
-// after the GPU budget was spent; tools/tc2_check.py is its bring-up harness (bit-identity against conv_tc).
+// layers: N = 256 accumulator columns when Cout % 256 == 0, N = 128 for the sub-pixel phase convolutions with 128
+// output channels.  Default since round 2 (bit-identical to conv_tc on tools/tc2_check.py and
+// tests/test_gpu_kernel_variants.py; 8-10 % faster per wide layer, profiles/r02_ab_pair_kernels.txt).
+//
+// Phase groups: the four sub-pixel phases of a stride-2 ConvTranspose / of a folded nearest-upsample + 3x3 conv are
+// four small-tap convolutions over the SAME input with their own weights, tap offsets and interleaved output view.
+// Launched one by one (round 1) each paid its own prologue, pipeline fill / drain and wave quantisation on few tiles
+// (25x25 maps: 4.2 waves of CTA pairs per launch); dreamb200_conv2d_fwd_phases runs them as ONE launch in which the
+// phase is simply the slowest tile coordinate -- per-phase weight / output tensor maps travel as kernel parameters.
 //
 // Why: the wide layers run with the tensor pipe 90-95 % active at the 1000 W power cap (SM clock 1.35 GHz), i.e. their
 // rate is set by energy per FLOP.  In a pair each CTA fetches only HALF of every weight tile: per k-block 16 KB (A) +
@@ -27,15 +34,22 @@ double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, i
 
 constexpr int kT2Split = 2;
 constexpr int kT2Threads = 64 + 128 * kT2Split;
-constexpr int kT2N = 256;
-constexpr int kT2BHalf = (kT2N / 2) * 128;                 // this CTA's half of a weight tile: 128 rows x 128 B
-constexpr int kT2StageBytes = kABytes + kT2BHalf;          // 32 KB
+constexpr int kT2MaxPhases = 4;
+constexpr int kNotEligible = -100;
 
-template <bool PLAIN>
+// per-phase tensor maps of one launch: weights [taps][Cout_pad][Cin] and the (possibly interleaved) output view
+struct PhaseMaps {
+  CUtensorMap b[kT2MaxPhases];
+  CUtensorMap c[kT2MaxPhases];
+};
+
+template <int kT2N, bool PLAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
-                const __grid_constant__ ConvParams p) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ PhaseMaps pm,
+                const __grid_constant__ CUtensorMap tmP, const __grid_constant__ ConvParams p) {
+  constexpr int kT2BHalf = (kT2N / 2) * 128;               // this CTA's half of a weight tile: N/2 rows x 128 B
+  constexpr int kT2StageBytes = kABytes + kT2BHalf;        // 32 KB (N = 256) / 24 KB (N = 128)
+  constexpr int kTmemCols = 2 * kT2N;                      // two accumulator stages
   constexpr uint32_t kIdesc = umma_idesc_f16_m256(kT2N);
 
   extern __shared__ uint8_t smem_raw[];
@@ -62,14 +76,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
+    for (int ph = 0; ph < (p.phases > 1 ? p.phases : 1); ++ph) {
+      tma_prefetch_desc(&pm.b[ph]);
+      tma_prefetch_desc(&pm.c[ph]);
+    }
     if (p.pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kT2Split); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_2sm<512>(tmem_ptr_smem);
+  if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -79,7 +95,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // pair-tile q -> output-channel tile n (fastest) and M-tile m = 2 * (q / n_tiles) + rank -> (tx, ty, b); an odd
   // M-tile count leaves the last pair's second tile at b == B: its loads are TMA zero fill, its stores clip away
-  auto decode = [&](int q, int& n, int& tx, int& ty, int& b) {
+  // (phase groups: the phase is the slowest coordinate, q = phase * tiles_per_phase + q')
+  auto decode = [&](int q, int& sp, int& n, int& tx, int& ty, int& b) {
+    sp = p.phases > 1 ? fast_div(q, p.mg_phase) : 0;
+    q -= sp * p.tiles_per_phase;
     const int t = fast_div(q, p.mg_n);
     n = q - t * p.n_tiles;
     const int m = 2 * t + (int)rank;
@@ -94,11 +113,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
-      int n, tx, ty, b;
-      decode(q, n, tx, ty, b);
+      int sp, n, tx, ty, b;                                   // sp = sub-pixel phase of a phase group (0 otherwise)
+      decode(q, sp, n, tx, ty, b);
       const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
+      const CUtensorMap* tmB = &pm.b[sp];
       for (int tap = 0; tap < p.taps; ++tap) {
-        const int xi = x0 + p.dx[tap], yi = y0 + p.dy[tap];
+        const int xi = x0 + p.dx[sp * p.taps + tap], yi = y0 + p.dy[sp * p.taps + tap];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_ab + stage * kT2StageBytes;
@@ -106,7 +126,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (rank == 0) mbar_expect_tx(full_bar(stage), (uint32_t)(2 * (p.tw * p.th * 128 + kT2BHalf)));
             const uint32_t bar = mapa_cluster(full_bar(stage), 0);
             tma_load_4d_2sm(sa, &tmA, bar, kc * 64, xi, yi, b);
-            tma_load_3d_2sm(sa + kABytes, &tmB, bar, kc * 64, n * kT2N + (int)rank * (kT2N / 2), tap);
+            tma_load_3d_2sm(sa + kABytes, tmB, bar, kc * 64, n * kT2N + (int)rank * (kT2N / 2), tap);
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
@@ -157,14 +177,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
-      int n, tx, ty, b;
-      decode(q, n, tx, ty, b);
+      int sp, n, tx, ty, b;
+      decode(q, sp, n, tx, ty, b);
       const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
       const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * kT2N);
-      epilogue_nhwc_tile<kT2N, kT2Split, true, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+      epilogue_nhwc_tile<kT2N, kT2Split, true, PLAIN>(p, &pm.c[sp], &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                       as ? tempty_l1 : tempty_l0, n, tx, ty, b, ox, oy, valid, row, lane,
                                                       epi_tid, chunk_ctr, hsel, csum);
       as ^= 1;
@@ -180,11 +200,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_2sm<512>(tmem_base);
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
   }
 }
 
-static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+template <int kT2N>
+static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream_t stream) {
+  constexpr int kT2BHalf = (kT2N / 2) * 128;
+  constexpr int kT2StageBytes = kABytes + kT2BHalf;
+  const dreamb200_conv_desc* d = descs;                     // phase 0 carries everything the phases share
   ConvParams p;
   memset(&p, 0, sizeof(p));
   conv_choose_tile(d->Wo, d->Ho, d->in_stride, d->y_pool != nullptr, &p.tw, &p.th);
@@ -196,9 +220,15 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d->B;
   const long long pairs = (m_tiles + 1) / 2;
-  DB_REQUIRE((m_tiles + 1) * p.n_tiles < (1ll << 24) && p.tiles_x < 65536 && p.tiles_y < 65536 && p.n_tiles < 65536,
+  DB_REQUIRE((m_tiles + 1) * p.n_tiles * n_phases < (1ll << 24) && p.tiles_x < 65536 && p.tiles_y < 65536 &&
+                 p.n_tiles < 65536,
              "conv: too many tiles for one launch (%d x %d x %d x %d)", p.tiles_x, p.tiles_y, p.n_tiles, d->B);
-  p.total_tiles = (int)(pairs * p.n_tiles);
+  // (fast_div is exact for divisors below 2^16: a phase group with more pair-tiles per phase goes phase by phase)
+  if (n_phases > 1 && pairs * p.n_tiles >= 65536) return kNotEligible;
+  p.phases = n_phases;
+  p.tiles_per_phase = (int)(pairs * p.n_tiles);
+  p.mg_phase = div_magic(p.tiles_per_phase);
+  p.total_tiles = p.tiles_per_phase * n_phases;
   p.absmax = d->absmax;
   p.gate = reinterpret_cast<const __half*>(d->gate);
   p.out_scale = d->out_scale;
@@ -209,8 +239,11 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.in_stride = d->in_stride;
   p.taps = d->taps;
   p.kchunks = d->Cin / 64;
-  memcpy(p.dy, d->tap_dy, sizeof(p.dy));
-  memcpy(p.dx, d->tap_dx, sizeof(p.dx));
+  for (int ph = 0; ph < n_phases; ++ph)
+    for (int t = 0; t < d->taps; ++t) {
+      p.dy[ph * d->taps + t] = descs[ph].tap_dy[t];
+      p.dx[ph * d->taps + t] = descs[ph].tap_dx[t];
+    }
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __half*>(d->residual);
   p.residual_f32 = d->residual_f32;
@@ -227,8 +260,9 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   p.stages = stages;
   const int smem_bytes = 1024 + stages * kT2StageBytes + out_bytes + 256 + kT2N * 4;
 
-  CUtensorMap tmA, tmB, tmC, tmP;
-  memset(&tmC, 0, sizeof(tmC));
+  CUtensorMap tmA, tmP;
+  PhaseMaps pm;
+  memset(&pm, 0, sizeof(pm));
   memset(&tmP, 0, sizeof(tmP));
   const uint32_t es4[4] = {1, 1, 1, 1};
   {
@@ -240,12 +274,21 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     DB_REQUIRE(box[1] <= 256 && box[2] <= 256, "conv_tc2: TMA box too large (%u x %u)", box[1], box[2]);
     if (make_tensor_map_f16(&tmA, d->x, 4, dims, str, box, es, "tc2 activation")) return -1;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->taps};
-    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
-    uint32_t box[3] = {64, (uint32_t)(kT2N / 2), 1};
-    uint32_t es[3] = {1, 1, 1};
-    if (make_tensor_map_f16(&tmB, d->w, 3, dims, str, box, es, "tc2 weights")) return -1;
+  for (int ph = 0; ph < n_phases; ++ph) {
+    const dreamb200_conv_desc* dp = descs + ph;
+    {
+      uint64_t dims[3] = {(uint64_t)dp->Cin, (uint64_t)dp->Cout_pad, (uint64_t)dp->taps};
+      uint64_t str[2] = {(uint64_t)dp->Cin * 2, (uint64_t)dp->Cout_pad * dp->Cin * 2};
+      uint32_t box[3] = {64, (uint32_t)(kT2N / 2), 1};
+      uint32_t es[3] = {1, 1, 1};
+      if (make_tensor_map_f16(&pm.b[ph], dp->w, 3, dims, str, box, es, "tc2 weights")) return -1;
+    }
+    if (dp->y != nullptr) {
+      uint64_t dims[4] = {(uint64_t)dp->Cout_pad, (uint64_t)dp->Wo, (uint64_t)dp->Ho, (uint64_t)dp->B};
+      uint64_t str[3] = {(uint64_t)dp->y_stride_w * 2, (uint64_t)dp->y_stride_h * 2, (uint64_t)dp->y_stride_b * 2};
+      uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+      if (make_tensor_map_f16(&pm.c[ph], dp->y, 4, dims, str, box, es4, "tc2 output")) return -1;
+    }
   }
   if (d->y_pool != nullptr) {
     const uint64_t Wp = (uint64_t)(d->Wo / 2), Hp = (uint64_t)(d->Ho / 2), C = (uint64_t)d->Cout_pad;
@@ -254,15 +297,9 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t box[4] = {64, (uint32_t)p.tw / 2, (uint32_t)p.th / 2, 1};
     if (make_tensor_map_f16(&tmP, d->y_pool, 4, dims, str, box, es4, "tc2 pooled output")) return -1;
   }
-  if (d->y != nullptr) {
-    uint64_t dims[4] = {(uint64_t)d->Cout_pad, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
-    uint64_t str[3] = {(uint64_t)d->y_stride_w * 2, (uint64_t)d->y_stride_h * 2, (uint64_t)d->y_stride_b * 2};
-    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
-    if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es4, "tc2 output")) return -1;
-  }
   const bool plain = d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
                      d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
-  auto kern = plain ? conv_tc2_kernel<true> : conv_tc2_kernel<false>;
+  auto kern = plain ? conv_tc2_kernel<kT2N, true> : conv_tc2_kernel<kT2N, false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[plain]) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -270,22 +307,53 @@ static int launch_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   }
   const int sms = device_sm_count() & ~1;
   const int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
-  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p);
+  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
+static bool tc2_enabled() {
+  // on by default since round 2; DREAMB200_TC2=0 switches back for A/B runs.  Read per call so a test can flip it.
+  const char* e = getenv("DREAMB200_TC2");
+  return !(e && e[0] == '0');
+}
+
 // Returns 1 and launches when the layer qualifies (and the kernel is switched on), 0 otherwise, <0 on error.
 int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream) {
-  // on by default since round 2 (bit-identical to conv_tc on every case of tools/tc2_check.py, 8-10 % faster per wide
-  // layer on a B200: profiles/r02_ab_pair_kernels.txt); DREAMB200_TC2=0 switches back for A/B runs.  Read per call so
-  // a test can flip it in-process.
-  const char* e = getenv("DREAMB200_TC2");
-  if (e && e[0] == '0') return 0;
-  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->Cout_pad % kT2N != 0) return 0;
+  if (!tc2_enabled()) return 0;
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->Cout_pad % 256 != 0) return 0;
   if ((long long)d->B * d->Ho * d->Wo < 2 * 128) return 0;            // fewer than two M-tiles: nothing to pair
-  const int rc = launch_tc2(d, stream);
+  const int rc = launch_tc2<256>(d, 1, stream);
+  return rc == 0 ? 1 : rc;
+}
+
+// A group of sub-pixel phase convolutions (same input, shapes, tap count and epilogue; own weights / tap offsets /
+// output view) as ONE launch.  Returns 1 when launched, 0 when the group does not qualify (the caller then launches
+// the phases one by one), <0 on error.
+int try_conv_tc2_phases(const dreamb200_conv_desc* descs, int n_phases, cudaStream_t stream) {
+  if (!tc2_enabled()) return 0;
+  { const char* e = getenv("DREAMB200_PHASE_GROUPS"); if (e && e[0] == '0') return 0; }
+  if (n_phases < 2 || n_phases > kT2MaxPhases) return 0;
+  const dreamb200_conv_desc* d = descs;
+  if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->Cout_pad % 128 != 0) return 0;
+  if ((long long)d->B * d->Ho * d->Wo < 2 * 128 || d->taps * n_phases > DREAMB200_MAX_TAPS) return 0;
+  if (d->y_pool || d->residual || d->residual_f32 || d->y_f32 || d->gate || d->out_scale || d->colsum || d->absmax)
+    return 0;
+  for (int ph = 1; ph < n_phases; ++ph) {
+    const dreamb200_conv_desc* q = descs + ph;
+    if (q->x != d->x || q->B != d->B || q->H != d->H || q->W != d->W || q->Cin != d->Cin ||
+        q->in_stride != d->in_stride || q->taps != d->taps || q->Cout_pad != d->Cout_pad || q->Ho != d->Ho ||
+        q->Wo != d->Wo || q->out_mode != d->out_mode || q->bias != d->bias || q->relu != d->relu ||
+        q->y_stride_w != d->y_stride_w || q->y_stride_h != d->y_stride_h || q->y_stride_b != d->y_stride_b ||
+        q->y == nullptr || q->y_pool || q->residual || q->residual_f32 || q->y_f32 || q->gate || q->out_scale ||
+        q->colsum || q->absmax)
+      return 0;
+  }
+  if (d->y == nullptr) return 0;
+  const int rc = d->Cout_pad % 256 == 0 ? launch_tc2<256>(descs, n_phases, stream)
+                                         : launch_tc2<128>(descs, n_phases, stream);
+  if (rc == kNotEligible) return 0;
   return rc == 0 ? 1 : rc;
 }
 

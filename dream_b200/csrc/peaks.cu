@@ -551,8 +551,8 @@ peaks_banded_kernel(const float* __restrict__ maps, const __grid_constant__ Gaus
     for (int x = lane; x < w; x += 32) bufA[r * w + x] = __ldg(srow + x);
   }
   __syncthreads();
-  // ---- axis 0: output row l (global y0-1+l) is centred on staged row l+13
-  gauss_strips(bufA, w, 1, bufB, 1, hp, rows_in, w, kFusedRadius + 1, rows_out, gw);
+  // ---- axis 0: staged row r is global row y0-13+r, so output row l (global y0-1+l) is centred on staged row l+12
+  gauss_strips(bufA, w, 1, bufB, 1, hp, rows_in, w, kFusedRadius, rows_out, gw);
   __syncthreads();
   // ---- axis 1: full rows, reflected at x = 0 / w like the whole-map kernel
   gauss_strips(bufB, hp, 1, bufA, hp, 1, w, rows_out, 0, w, gw);

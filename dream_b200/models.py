@@ -178,9 +178,9 @@ def _run_deconv(pc, x):
     Ho, Wo = 2 * H, 2 * W
     y = torch.empty((B, Ho, Wo, cpad), dtype=torch.float16, device=x.device)
     strides = (2 * cpad, 2 * Wo * cpad, Ho * Wo * cpad)
-    for py, px, w, taps in pc.phases:
-        ops.conv_taps(x, w, pc.b, taps, H, W, relu=pc.relu, y=y, y_strides=strides,
-                      y_offset=(py * Wo + px) * cpad)
+    # the four phases go to the library as one group: one launch when they are uniform (dreamb200_conv2d_fwd_phases)
+    ops.conv_phases(x, [((py * Wo + px) * cpad, w, taps) for py, px, w, taps in pc.phases], pc.b, H, W, y, strides,
+                    relu=pc.relu)
     return y
 
 
@@ -523,10 +523,6 @@ class ResnetSimple(_PlanModule):
             from . import pretrained as _pretrained
             _pretrained.load_resnet101_trunk(self)
 
-    # bytes of ONE stage tensor (fp32 + fp16 copy) a batch chunk of the bottleneck stages may occupy: in + out of a
-    # block then take twice that, which has to fit the 126 MB L2 with room for weights; 0 disables the blocking
-    l2_block_bytes = int(float(__import__("os").environ.get("DREAMB200_L2_BLOCK_MB", "0")) * 1e6)
-
     def _n(self, key):
         return _node_for(self, key)
 
@@ -564,33 +560,23 @@ class ResnetSimple(_PlanModule):
         t = ops.maxpool(t, 3, 2, 1)
         # The identity stream of the 33 bottlenecks stays fp32 (t32) next to the fp16 copy (t) that feeds
         # the tensor cores: rounding the trunk to fp16 at every block random-walks past the 1e-3 gate.
-        # L2 blocking: the bottleneck stages are HBM-bound on the fp32 identity stream (a 1x1 expansion reads and
-        # writes 6 bytes per output element for 2*Cin MACs).  Run each stage on batch CHUNKS small enough that one
-        # block's stream (fp32 + fp16, in and out) stays inside the 126 MB L2 from the layer that writes it to the
-        # layers that read it, all blocks of the stage per chunk; chunks are contiguous NHWC slices, no copies.
-        B = t.shape[0]
+        # (Tried in round 2 and dropped: running each stage on batch chunks sized for the 126 MB L2 so that the fp32
+        #  stream stays on chip.  Same-box: resnet-H 12.9 -> 16.6 ms (120 MB chunks) / 22.4 ms (40 MB), resnet-F
+        #  9.9 -> 14.8 ms -- 3-8x more launches with too few tiles each cost far more than the saved HBM traffic;
+        #  profiles/r02_resnet_l2_blocking.txt.)
+        t32 = None
         for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
-            planes4 = 256 * 2 ** (li - 1)
-            Hs, Ws = (t.shape[1], t.shape[2]) if li == 1 else ((t.shape[1] - 1) // 2 + 1, (t.shape[2] - 1) // 2 + 1)
-            per_image = Hs * Ws * planes4 * 6                       # fp32 + fp16 copy of one stage tensor
-            chunk = B if self.l2_block_bytes <= 0 else max(1, min(B, int(self.l2_block_bytes // per_image)))
-            out16 = torch.empty((B, Hs, Ws, planes4), dtype=torch.float16, device=t.device) if chunk < B else None
-            for b0 in range(0, B, chunk):
-                tc, tc32 = t[b0:b0 + chunk], None
-                for bi in range(nblocks):
-                    k = "layer%d.%d" % (li, bi)
-                    idn32 = _run_conv(P[k + ".down"], tc, want_f32=True)[1] if bi == 0 else tc32
-                    o = _run_conv(P[k + ".conv1"], tc)
-                    o = _run_conv(P[k + ".conv2"], o)
-                    if bi == nblocks - 1:
-                        # last block of the stage: only the fp16 tensor is read again (the next stage's identity comes
-                        # from its own downsample conv), so no fp32 copy is written; chunks land in the full-batch tensor
-                        pc = P[k + ".conv3"]
-                        tc = ops.conv_taps(o, pc.w, pc.b, pc.taps, Hs, Ws, relu=pc.relu, residual_f32=idn32,
-                                           y=out16[b0:b0 + chunk] if out16 is not None else None)
-                    else:
-                        tc, tc32 = _run_conv(P[k + ".conv3"], o, residual_f32=idn32, want_f32=True)  # relu(bn3+identity)
-            t = out16 if out16 is not None else tc
+            for bi in range(nblocks):
+                k = "layer%d.%d" % (li, bi)
+                idn32 = _run_conv(P[k + ".down"], t, want_f32=True)[1] if bi == 0 else t32
+                o = _run_conv(P[k + ".conv1"], t)
+                o = _run_conv(P[k + ".conv2"], o)
+                if bi == nblocks - 1:
+                    # last block of a stage: only the fp16 tensor is read again (the next stage's identity comes from
+                    # its own downsample conv), so no fp32 copy is written
+                    t = _run_conv(P[k + ".conv3"], o, residual_f32=idn32)
+                else:
+                    t, t32 = _run_conv(P[k + ".conv3"], o, residual_f32=idn32, want_f32=True)  # relu(bn3+identity)
         for i in range(4):
             t = _run_deconv(P["up%d" % i], t)
         if self.full:

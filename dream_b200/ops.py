@@ -130,6 +130,45 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
     return y
 
 
+def conv_phases(x, phases, bias, Ho, Wo, y, y_strides, relu=False, stride=1):
+    """The sub-pixel phases of a stride-2 ConvTranspose / folded upsample + conv as one call
+    (dreamb200_conv2d_fwd_phases): `phases` = [(element offset into y, w [T,Cout_pad,Cin] fp16, taps [(dy,dx)])], all
+    writing the same interleaved view (`y_strides`) of `y` from the same input.  One launch when the group is uniform
+    (CTA-pair kernel, Cout_pad % 128 == 0), otherwise one launch per phase -- identical results."""
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4
+    B, H, W_, Cin = x.shape
+    n = len(phases)
+    assert 1 <= n <= 4
+    descs = (ConvDesc * n)()
+    for i, (y_offset, w, taps) in enumerate(phases):
+        assert w.dtype == torch.float16 and w.is_contiguous() and w.dim() == 3 and w.shape[2] == Cin and w.shape[0] == len(taps)
+        d = descs[i]
+        d.x = x.data_ptr(); d.B = B; d.H = H; d.W = W_; d.Cin = Cin; d.in_stride = stride
+        d.w = w.data_ptr(); d.bias = bias.data_ptr() if bias is not None else None
+        d.taps = len(taps); d.Cout_pad = w.shape[1]
+        for t, (dy, dx) in enumerate(taps):
+            d.tap_dy[t] = dy; d.tap_dx[t] = dx
+        d.Ho = Ho; d.Wo = Wo
+        d.out_mode = _lib.OUT_NHWC_F16; d.cout_real = w.shape[1]
+        d.y_stride_w, d.y_stride_h, d.y_stride_b = y_strides
+        d.y = y.data_ptr() + y_offset * y.element_size()
+        d.relu = 1 if relu else 0
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().dreamb200_conv2d_fwd_phases(descs, n, _stream()), "dreamb200_conv2d_fwd_phases")
+    if PROFILE is not None:
+        e1.record()
+        Cout_pad = phases[0][1].shape[1]
+        T = sum(len(p[2]) for p in phases)
+        uniform = len({len(p[2]) for p in phases}) == 1 and Cout_pad % 128 == 0 and n > 1 and \
+            os.environ.get("DREAMB200_TC2", "1")[:1] != "0" and os.environ.get("DREAMB200_PHASE_GROUPS", "1")[:1] != "0"
+        tag = "%s<%d> %dxT%d Cin%d Cout%d %dx%d s%d" % ("conv_tc2" if uniform else "conv_phases", 256 if Cout_pad % 256 == 0 else 128,
+                                                        n, T // n, Cin, Cout_pad, Ho, Wo, stride)
+        PROFILE.append((tag, 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
+    return y
+
+
 def _norm3(v):
     a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float32).reshape(-1), (3,)))
     return a

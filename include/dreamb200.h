@@ -83,6 +83,12 @@ int dreamb200_version(void);
 int64_t dreamb200_launch_count(void);
 
 int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream);
+/* The sub-pixel phases of a stride-2 ConvTranspose2d (dream/models.py:618-686, 37-136) or of nn.Upsample(2) + 3x3 conv
+   (models.py:691-709) are `n_phases` (<= 4) convolutions over the same input with their own weights, tap offsets and
+   interleaved output view: descs[0..n_phases).  When the group is uniform (same shapes / tap count / epilogue, plain
+   bias + ReLU) and Cout_pad % 128 == 0 it runs as ONE launch; otherwise exactly like n_phases dreamb200_conv2d_fwd
+   calls.  Results are identical either way. */
+int dreamb200_conv2d_fwd_phases(const dreamb200_conv_desc* descs, int n_phases, void* stream);
 
 /* The network's first conv (3->64, 3x3 s1 p1, +bias +ReLU; models.py:591-599) fused with the input pack:
    x fp32 NCHW [B,3,H,W], w fp16 [1][64][64] (k=(r*3+s)*3+c, zero padded), bias fp32 [64] -> y fp16 NHWC [B,H,W,64] */

@@ -294,22 +294,35 @@ def test_cuda_graph_inference_is_bit_identical_to_eager_and_follows_the_weights(
     assert np.array_equal(ra["detected_keypoints"], rb["detected_keypoints"])
 
 
-@pytest.mark.parametrize("full", [False, True])
-def test_resnet_l2_blocked_stages_are_bit_identical_to_whole_batch(full, built_lib):
-    """ResnetSimple.belief_maps runs the bottleneck stages on batch chunks sized for the L2 (models.py); every image
-    is computed by the same tiles either way, so the belief maps must not change by a bit -- whatever the chunk size."""
+@pytest.mark.parametrize("kind,shape", [("vgg_q", (3, 3, 200, 200)), ("vgg_q", (2, 3, 104, 72)), ("vgg_f", (2, 3, 96, 128)),
+                                        ("resnet_h", (2, 3, 160, 192)), ("resnet_f", (1, 3, 96, 128))])
+def test_phase_groups_are_bit_identical_to_phase_by_phase_launches(kind, shape, built_lib):
+    """dreamb200_conv2d_fwd_phases: the four sub-pixel phases of a folded upsample + conv (vgg-Q: 512 -> 256 on the
+    CTA-pair N = 256 kernel, 256 -> 128 on its N = 128 form), of ConvTranspose(4,2,1) (resnet, 256 channels) and of
+    ConvTranspose(3,2,1,1) (vgg-F: 1/2/2/4 taps -- NOT uniform, must fall back) as one launch vs one launch per phase
+    vs the single-CTA kernel: the belief maps must not change by a bit."""
     from dream_b200 import models
     from oracle import ref_models
-    sd = ref_models.synth_state_dict(ref_models.resnet_state_shapes(7, full=full, prefix=""), seed=2, out_gain=0.05,
-                                     mode="he")
-    net = models.ResnetSimple(7, full=full, pretrained=False)
+    if kind.startswith("vgg"):
+        kw = dict(deconv_decoder=True, full_output=True) if kind == "vgg_f" else {}
+        sd = ref_models.synth_state_dict(ref_models.vgg_state_shapes(7, prefix="", **kw), seed=2, out_gain=13.0, mode="default")
+        net = models.DreamHourglass(7, internalize_spatial_softmax=False, **kw)
+    else:
+        full = kind == "resnet_f"
+        sd = ref_models.synth_state_dict(ref_models.resnet_state_shapes(7, full=full, prefix=""), seed=2, out_gain=0.05, mode="he")
+        net = models.ResnetSimple(7, full=full, pretrained=False)
     net.load_state_dict(sd)
     net = net.cuda().eval()
-    x = (torch.rand((5, 3, 96, 128), generator=torch.Generator().manual_seed(0)) * 2 - 1).cuda()
-    outs = []
+    x = (torch.rand(shape, generator=torch.Generator().manual_seed(0)) * 2 - 1).cuda()
+    from dream_b200 import _lib
+    outs, launches = [], []
     with torch.no_grad():
-        for mb in (0, 40e6, 0.3e6, 0.05e6):          # off, default, chunks of a few images, chunks of one image
-            net.l2_block_bytes = int(mb)
-            outs.append(net.belief_maps(x).clone())
-    for o in outs[1:]:
-        assert torch.equal(outs[0], o)
+        net.belief_maps(x)                           # packs the weights
+        for groups, tc2 in (("1", "1"), ("0", "1"), ("0", "0")):
+            with env(DREAMB200_PHASE_GROUPS=groups, DREAMB200_TC2=tc2):
+                n0 = _lib.launch_count()
+                outs.append(net.belief_maps(x).clone())
+                launches.append(_lib.launch_count() - n0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    if kind != "vgg_f":
+        assert launches[0] < launches[1], launches   # the groups really ran as fewer launches
