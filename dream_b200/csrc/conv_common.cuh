@@ -112,6 +112,88 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
     const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
     const uint32_t pbuf = smem_pool + (chunk_ctr & 1u) * kPoolBytes;
+    if constexpr (PLAIN) {
+      if (shfl_pool && !p.store_full) {
+        // Pool-only tiles (every pooled layer in inference): max FIRST, on the fp32 accumulators, then bias + ReLU +
+        // fp16 on the pooled quarter only.  Bit-identical to pooling the finished fp16 values -- x -> fp16(relu(x + b))
+        // is monotonic, so it commutes with max -- at less than half the instructions: the 2x2 window's four lanes
+        // (l, l^1, l^tw, l^tw^1) swap HALVES of their 32 columns (16 + 8 shuffles) so each ends up owning 8 pooled
+        // channels, instead of every lane finishing all 32 channels and three of four throwing them away.
+        uint32_t packed[2 / SPLIT][4];
+        const uint32_t odd = (uint32_t)lane & 1u, up = ((uint32_t)lane & (uint32_t)p.tw) ? 1u : 0u;
+#pragma unroll
+        for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+          const int h = SPLIT == 2 ? hsel : hh;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + h * 32), v);
+          tmem_wait_ld();
+          float a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float send = __uint_as_float(odd ? v[i] : v[16 + i]);
+            const float keep = __uint_as_float(odd ? v[16 + i] : v[i]);
+            a[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+          }
+          float q[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float send = up ? a[i] : a[8 + i];
+            const float keep = up ? a[8 + i] : a[i];
+            q[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tw));
+          }
+          if (p.bias != nullptr) {
+            const uint32_t bias_addr = smem_bias + (uint32_t)(c * 64 + h * 32 + (int)(odd * 16u + up * 8u)) * 4u;
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+              float b0, b1, b2, b3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bias_addr + (uint32_t)i * 4u));
+              q[i] += b0; q[i + 1] += b1; q[i + 2] += b2; q[i + 3] += b3;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = fmaxf(q[i], 0.0f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) packed[hh][i] = pack_h2(q[2 * i], q[2 * i + 1]);
+        }
+        if (c == BLOCK_N / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CLUSTER_ARRIVE) mbar_arrive_cluster(tempty_bar_addr); else mbar_arrive(tempty_bar_addr);
+          }
+        }
+        if (epi_tid < 32) {                              // the store that used pbuf two chunks ago has read it
+          if (elect_one()) tma_store_wait_read<1>();
+        }
+        named_bar_sync(1, kEpiThreads);
+        {
+          const int sh = p.tw == 8 ? 3 : 4;
+          const int ly = row >> sh, lx = row & (p.tw - 1);
+          const uint32_t pr = (uint32_t)((ly >> 1) * (p.tw >> 1) + (lx >> 1));
+#pragma unroll
+          for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+            const uint32_t h = SPLIT == 2 ? (uint32_t)hsel : (uint32_t)hh;
+            const uint32_t j = h * 4u + odd * 2u + up;    // 16-byte chunk (8 channels) of the pooled pixel's row
+            const uint32_t dst = pbuf + pr * 128u + ((j ^ (pr & 7u)) * 16u);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[hh][0]), "r"(packed[hh][1]),
+                         "r"(packed[hh][2]), "r"(packed[hh][3])
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (epi_tid < 32) {
+          if (elect_one()) {
+            tma_store_4d(tmP, pbuf, n * BLOCK_N + c * 64, tx * (p.tw >> 1), ty * (p.th >> 1), b);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
+    }
     uint32_t hv[kRegs];                                // this thread's output channels of the pixel, packed fp16
 #pragma unroll
     for (int hh = 0; hh < 2 / SPLIT; ++hh) {

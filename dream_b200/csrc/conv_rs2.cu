@@ -374,7 +374,12 @@ int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1) return 0;
   const double util = (double)d->Wo * d->Ho /
                       ((double)((d->Wo + kR2Tw - 1) / kR2Tw) * ((d->Ho + 2 * kR2Th - 1) / (2 * kR2Th)) * 256.0);
-  if (util < 0.8) return 0;
+  static double min_util = -1.0;
+  if (min_util < 0.0) {
+    const char* e = getenv("DREAMB200_RS2_MIN_UTIL");       // A/B knob: how empty the last pair of tile rows may be
+    min_util = e ? atof(e) : 0.8;
+  }
+  if (util < min_util) return 0;
   const int kchunks = d->Cin / 64;
   // resident half tiles need room for at least two activation slabs next to them
   const int out_bytes = 2 * kStageOutBytes + (d->y_pool != nullptr ? 2 * kPoolBytes : 0);
