@@ -108,6 +108,24 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   }
   const bool shfl_pool = p.pool && (p.tw == 8 || p.tw == 16);
   const bool write_full = !p.pool || p.store_full || !shfl_pool;
+  // fp32 identity stream (ResNet bottlenecks): the 1x1 expansion layers are HBM-bound on this read -- 4 bytes per
+  // output element against 2 * Cin MACs -- and the loads used to be issued only after the TMEM read of the same
+  // chunk, one dependent round trip per 64 columns.  Now the residual of chunk c+1 is in flight while chunk c is
+  // converted, stored and handed to the TMA (double-buffered in registers).
+  float4 rpre[2 / SPLIT][8];
+  auto prefetch_res32 = [&](int c) {
+#pragma unroll
+    for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+      const int h = SPLIT == 2 ? hsel : hh;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        rpre[hh][i] = res32_row != nullptr ? __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32) + i)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if constexpr (!PLAIN) {
+    if (p.residual_f32 != nullptr) prefetch_res32(0);
+  }
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
     const uint32_t obuf = smem_out + (chunk_ctr & 1u) * kStageOutBytes;
@@ -237,12 +255,13 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
           }
         }
       }
-      if (!PLAIN && res32_row != nullptr) {
+      if (!PLAIN && p.residual_f32 != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(res32_row + c * 64 + h * 32 + i));
+          const float4 rv = rpre[hh][i >> 2];
           f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
         }
+        if (hh == 2 / SPLIT - 1 && c + 1 < BLOCK_N / 64) prefetch_res32(c + 1);
       }
       if (p.relu) {
 #pragma unroll

@@ -363,7 +363,7 @@ int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     // tiles per barrier; one tile per barrier was SLOWER than conv_rs, 1.60 ms); 64 -> 128 unchanged (0.58 ms) -- so
     // bits 0 and 1 are on by default.
     const char* e = getenv("DREAMB200_RS2");
-    mode = e ? atoi(e) : 3;
+    mode = e ? atoi(e) : 7;      // round 2: bit 2 on too (128 -> 64 @100x100: 0.284 -> 0.233 ms, profiles/r02_ab_rs2_tail.txt)
   }
   if (mode == 0) return 0;
   if (d->out_mode != DREAMB200_OUT_NHWC_F16 || d->taps != 9 || d->in_stride != 1) return 0;
@@ -377,7 +377,7 @@ int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   static double min_util = -1.0;
   if (min_util < 0.0) {
     const char* e = getenv("DREAMB200_RS2_MIN_UTIL");       // A/B knob: how empty the last pair of tile rows may be
-    min_util = e ? atof(e) : 0.8;
+    min_util = e ? atof(e) : 0.7;   // 100x100 maps fill 75 % of their tile pairs and still gain (64 -> 64: 0.156 -> 0.128 ms)
   }
   if (util < min_util) return 0;
   const int kchunks = d->Cin / 64;

@@ -553,6 +553,8 @@ class ResnetSimple(_PlanModule):
         return P
 
     def belief_maps(self, x):
+        if self.precise:
+            return self.belief_maps_precise(x)
         x = self._check_input(x)
         P = self.plan()
         t = ops.im2col_first(x, 7, 7, 2, 3, 192)
@@ -582,6 +584,137 @@ class ResnetSimple(_PlanModule):
         if self.full:
             t = _run_deconv(P["up4"], t)
         return _run_conv(P["head"], t, head_cout=self.n_keypoints)
+
+    # ------------------------------------------------------------------------------------------
+    # precise mode: split-fp16 operands (x = hi + lo, w = hi + lo; three of the four products)
+    # ------------------------------------------------------------------------------------------
+    # Tensor-core operands carry 11 significant bits (fp16, and TF32 alike).  On weights that keep every one of the
+    # 104 layers O(1) that format alone puts the belief maps 1.1e-3 .. 1.7e-3 from the fp32 reference (the oracle run
+    # with nothing but fp16-rounded operands is that far off, tests/test_gpu_parity.py), i.e. the default path sits at
+    # the format's floor but outside BASELINE's 1e-3.  `precise = True` (or DREAMB200_PRECISE=1) buys the bits back
+    # with the SAME kernels: every activation is kept in fp32 and split into hi = fp16(a), lo = fp16(a - hi); the conv
+    # runs over 3*Cin channels [a_hi | a_lo | a_hi] against [w_hi | w_hi | w_lo], i.e. a_hi w_hi + a_lo w_hi + a_hi w_lo
+    # (the dropped lo*lo term is 2^-22), accumulating in fp32 in TMEM and leaving through the fp32 epilogue output.
+    # 3x the MMA work and fp32 activation traffic: a parity / validation mode, not the benchmarked path.
+    precise = __import__("os").environ.get("DREAMB200_PRECISE", "0") == "1"
+
+    @staticmethod
+    def _split3(t32):
+        """fp32 NHWC [..., C] -> fp16 [..., 3C] = [hi | lo | hi]"""
+        hi = t32.half()
+        lo = (t32 - hi.float()).half()
+        return torch.cat([hi, lo, hi], dim=-1).contiguous()
+
+    @staticmethod
+    def _precise_pack(w_oihw, rs, scale, cin_pad=None, cout_pad=None, first=False):
+        wf = w_oihw.detach().float()
+        if scale is not None:
+            wf = wf * scale.view(-1, 1, 1, 1)
+        hi = wf.half().float()
+        lo = wf - hi
+        if first:                                         # 7x7 stem: im2col'ed patches, k = (r*S+s)*3+c padded to 192
+            ph, pl = ops.pack_first_weight(hi, 192, cout_pad=cout_pad), ops.pack_first_weight(lo, 192, cout_pad=cout_pad)
+        else:
+            ph = ops.pack_conv_weight(hi, rs, cin_pad=cin_pad, cout_pad=cout_pad)
+            pl = ops.pack_conv_weight(lo, rs, cin_pad=cin_pad, cout_pad=cout_pad)
+        return torch.cat([ph, ph, pl], dim=2).contiguous()
+
+    def _precise_plan(self):
+        key = self._version_key()
+        if getattr(self, "_pp", None) is not None and self._pp_key == key:
+            return self._pp
+        n = self._n
+        P = {}
+        with torch.no_grad():
+            def conv(key_, bn_key, relu, stride=1, cout_pad=None):
+                node, bn = n(key_), (n(bn_key) if bn_key else None)
+                scale, bias = (None, node.bias) if bn is None else _bn_scale_shift(bn, node.bias)
+                ksz = node.weight.shape[2]
+                rs = [(r, s_) for r in range(ksz) for s_ in range(ksz)]
+                w3 = self._precise_pack(node.weight, rs, scale, cout_pad=cout_pad)
+                taps = [(r - ksz // 2, s_ - ksz // 2) for r, s_ in rs]
+                return _PackedConv(w3, ops.pad_bias(bias, w3.shape[1], w3.device), taps, stride=stride, relu=relu,
+                                   cout=node.weight.shape[0])
+
+            def deconv(key_, bn_key):
+                node, bn = n(key_), n(bn_key)
+                scale, bias = _bn_scale_shift(bn, node.bias)
+                w_oihw = node.weight.detach().permute(1, 0, 2, 3)
+                phases = []
+                for py in range(2):
+                    for px in range(2):
+                        ty, tx = _deconv_phase_taps(4, py), _deconv_phase_taps(4, px)
+                        rs = [(ky, kx) for (_, ky) in ty for (_, kx) in tx]
+                        taps = [(dy, dx) for (dy, _) in ty for (dx, _) in tx]
+                        phases.append((py, px, self._precise_pack(w_oihw, rs, scale), taps))
+                cout = w_oihw.shape[0]
+                return _PackedConv(None, ops.pad_bias(bias, ops.round_up(cout, 64), node.weight.device), None, relu=True,
+                                   cout=cout, phases=phases)
+            scale, shift = _bn_scale_shift(n("bn1"), None)
+            w3 = self._precise_pack(n("conv1").weight, None, scale, first=True)
+            P["conv1"] = _PackedConv(w3, ops.pad_bias(shift, 64, w3.device), [(0, 0)], relu=True, cout=64)
+            for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
+                for bi in range(nblocks):
+                    k = "layer%d.%d" % (li, bi)
+                    stride = 2 if (li > 1 and bi == 0) else 1
+                    P[k + ".conv1"] = conv(k + ".conv1", k + ".bn1", True)
+                    P[k + ".conv2"] = conv(k + ".conv2", k + ".bn2", True, stride=stride)
+                    P[k + ".conv3"] = conv(k + ".conv3", k + ".bn3", True)
+                    if bi == 0:
+                        P[k + ".down"] = conv(k + ".downsample.0", k + ".downsample.1", False, stride=stride)
+            for i in range(4):
+                P["up%d" % i] = deconv("upsample.%d" % (3 * i), "upsample.%d" % (3 * i + 1))
+            if self.full:
+                P["up4"] = deconv("upsample2.0", "upsample2.1")
+                P["head"] = conv("upsample2.3", None, False, cout_pad=16)
+            else:
+                P["head"] = conv("upsample.12", None, False, cout_pad=16)
+        self._pp, self._pp_key = P, key
+        return P
+
+    def belief_maps_precise(self, x):
+        x = self._check_input(x)
+        P = self._precise_plan()
+
+        def run(pc, t32, residual_f32=None):
+            B, H, W, _ = t32.shape
+            Ho, Wo = (H, W) if pc.stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+            y32 = torch.empty((B, Ho, Wo, pc.w.shape[1]), dtype=torch.float32, device=t32.device)
+            ops.conv_taps(self._split3(t32), pc.w, pc.b, pc.taps, Ho, Wo, stride=pc.stride, relu=pc.relu,
+                          residual_f32=residual_f32, y_f32=y32)
+            return y32
+
+        def run_deconv(pc, t32):
+            B, H, W, _ = t32.shape
+            cpad = pc.b.numel()
+            x3 = self._split3(t32)
+            out = torch.empty((B, 2 * H, 2 * W, cpad), dtype=torch.float32, device=t32.device)
+            for py, px, w3, taps in pc.phases:
+                y32 = torch.empty((B, H, W, cpad), dtype=torch.float32, device=t32.device)
+                ops.conv_taps(x3, w3, pc.b, taps, H, W, relu=pc.relu, y_f32=y32)
+                out[:, py::2, px::2] = y32
+            return out
+        # stem: fp16 patches of x_hi and x_lo, 3 x 192 channels
+        x_hi = x.half().float()
+        p_hi, p_lo = ops.im2col_first(x_hi, 7, 7, 2, 3, 192), ops.im2col_first(x - x_hi, 7, 7, 2, 3, 192)
+        pc = P["conv1"]
+        B, Ho, Wo, _ = p_hi.shape
+        t32 = torch.empty((B, Ho, Wo, 64), dtype=torch.float32, device=x.device)
+        ops.conv_taps(torch.cat([p_hi, p_lo, p_hi], dim=-1).contiguous(), pc.w, pc.b, pc.taps, Ho, Wo, relu=True, y_f32=t32)
+        t32 = nn.functional.max_pool2d(t32.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
+            for bi in range(nblocks):
+                k = "layer%d.%d" % (li, bi)
+                idn = run(P[k + ".down"], t32) if bi == 0 else t32
+                o = run(P[k + ".conv2"], run(P[k + ".conv1"], t32))
+                t32 = run(P[k + ".conv3"], o, residual_f32=idn)
+        for i in range(4):
+            t32 = run_deconv(P["up%d" % i], t32)
+        if self.full:
+            t32 = run_deconv(P["up4"], t32)
+        pc = P["head"]
+        return ops.conv_taps(self._split3(t32), pc.w, pc.b, pc.taps, t32.shape[1], t32.shape[2],
+                             head_cout=self.n_keypoints)
 
     def forward(self, x):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):

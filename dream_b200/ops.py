@@ -115,11 +115,11 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
                 os.environ.get("DREAMB200_TC2", "1")[:1] != "0"):      # mirror of try_conv_tc2 (conv_tc2.cu)
             fam = "conv_tc2"
         if rs and head_cout is None and Ho >= 32:      # mirror of try_conv_rs2 (conv_rs2.cu): the CTA-pair slab kernel
-            mode = int(os.environ.get("DREAMB200_RS2", "3"))
+            mode = int(os.environ.get("DREAMB200_RS2", "7"))
             pair_util = Ho * Wo / (((Wo + 7) // 8) * ((Ho + 31) // 32) * 256.0)
             want = (mode & 1) if (Cout_pad == 64 and Cin == 64) else (mode & 4) if Cout_pad == 64 else \
                    ((mode & 8) if Cin == 64 else (mode & 2)) if Cout_pad == 128 else 0
-            if want and pair_util >= float(os.environ.get("DREAMB200_RS2_MIN_UTIL", 0.8)):
+            if want and pair_util >= float(os.environ.get("DREAMB200_RS2_MIN_UTIL", 0.7)):
                 fam = "conv_rs2"
         tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % (fam, block_n, T, Cin, Cout_pad, Ho, Wo, stride)
         PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))

@@ -211,6 +211,35 @@ def test_state_dict_round_trip_with_module_prefix(built_lib):
     assert list(mr.state_dict().keys()) == list(sdr.keys())
 
 
+@pytest.mark.parametrize("name,shape", [("resnet_h_he", None), ("resnet_f_he", None), ("resnet_h_he", (2, 3, 400, 400)),
+                                        ("resnet_f_he", (1, 3, 480, 640))])
+def test_resnet_precise_mode_meets_the_1e3_gate(name, shape, golden_dir, built_lib):
+    """BASELINE's gate for configs 3 and 5: belief maps within 1e-3 max-abs of the fp32 reference.  The default path
+    runs 11-bit tensor-core operands and sits at that format's floor (1.1e-3 .. 1.7e-3 on these He-scaled stress
+    weights, STRESS_TOL above); `precise = True` (split-fp16 operands, same kernels, 3x the MMA work) must meet 1e-3
+    with a wide margin -- on the reference-generated golden fixtures and at the BASELINE resolutions vs the oracle."""
+    if shape is None:
+        g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+        sd = ref_models.synth_state_dict(_shapes(name), seed=0, out_gain=float(g["gain"]), mode="he")
+        x, ref = torch.from_numpy(g["x"]), g["y"]
+    else:
+        x = torch.rand(shape, generator=torch.Generator().manual_seed(5)) * 2 - 1
+        sd = ref_models.synth_state_dict(_shapes(name), seed=1, mode="he")
+        gain = 1.0 / _oracle(name, sd, x[:1]).abs().max().item()
+        sd = ref_models.synth_state_dict(_shapes(name), seed=1, out_gain=gain, mode="he")
+        ref = _oracle(name, sd, x).numpy()
+    net = _build(name, sd)
+    with torch.no_grad():
+        fast = net(x.cuda())[0].cpu().numpy()
+        net.precise = True
+        y = net(x.cuda())[0].cpu().numpy()
+    err, err_fast = np.abs(y - ref).max(), np.abs(fast - ref).max()
+    print("%s %s precise max-abs %.3g (default path %.3g, ref max %.3g)" % (name, shape, err, err_fast, np.abs(ref).max()))
+    assert y.shape == ref.shape
+    assert err <= BELIEF_TOL * max(1.0, np.abs(ref).max()) / 10, err       # 1e-4: ten times inside the gate
+    assert err < err_fast
+
+
 def _flat(peaks):
     return np.array([(j, p[0], p[1], float(p[2]), p[3]) for j, lst in enumerate(peaks) for p in lst],
                     dtype=np.float64).reshape(-1, 5)
