@@ -35,6 +35,7 @@ struct ConvParams {
   // the tap tables above then hold phases * taps entries, phase-major.  0 / 1 = an ordinary convolution.
   int phases, tiles_per_phase;
   unsigned long long mg_phase;
+  int res_slots;    // conv_tc2: > 0 = the fp32 residual is staged through a shared-memory ring of this many chunk slots
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
@@ -62,6 +63,20 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 
+// fp32 residual tiles staged in shared memory by the TMA producer warp (conv_tc2.cu): a ring of `slots` chunk slots,
+// each two 128-row x 32-float sub-tiles (16 KB, SWIZZLE_128B) = the residual of one 64-column output chunk.  Every
+// epilogue warp keeps its own (idx, phase) cursor; a slot is handed back once all `4 * SPLIT` warps have read it.
+struct ResRing {
+  uint32_t smem;          // shared address of slot 0 (1024-byte aligned)
+  uint32_t full_bar;      // mbarrier of slot 0 (TMA transaction bytes); slot s at + 8 * s
+  uint32_t empty_bar;     // mbarrier of slot 0 (count = epilogue warps)
+  int slots;
+  int idx;
+  uint32_t phase;
+};
+constexpr uint32_t kResSubBytes = 128 * 128;            // one sub-tile: 128 rows x 32 fp32
+constexpr uint32_t kResSlotBytes = 2 * kResSubBytes;
+
 // One output tile (128 accumulator rows x BLOCK_N columns) of the NHWC fp16 path; called by the 4 epilogue
 // warps (128 threads, named barrier 1).  `t_row` = TMEM address of this thread's lane quarter / accumulator stage,
 // `smem_bias` = shared-memory copy of the current channel tile's fp32 bias (BLOCK_N floats, zeros when none).
@@ -83,7 +98,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
                                                    int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
                                                    int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0,
-                                                   float* csum = nullptr, const float* breg = nullptr) {
+                                                   float* csum = nullptr, const float* breg = nullptr,
+                                                   ResRing* rr = nullptr) {
   constexpr int kEpiThreads = 128 * SPLIT;
   constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
@@ -124,7 +140,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     }
   };
   if constexpr (!PLAIN) {
-    if (p.residual_f32 != nullptr) prefetch_res32(0);
+    if (p.residual_f32 != nullptr && rr == nullptr) prefetch_res32(0);
   }
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
@@ -255,7 +271,25 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
           }
         }
       }
-      if (!PLAIN && p.residual_f32 != nullptr) {
+      if (!PLAIN && p.residual_f32 != nullptr && rr != nullptr) {
+        // residual chunk staged by the producer warp: this thread's 32 floats are 8 swizzled 16-byte pieces of its row
+        if (hh == 0) mbar_wait(rr->full_bar + 8u * (uint32_t)rr->idx, rr->phase);
+        const uint32_t rbase = rr->smem + (uint32_t)rr->idx * kResSlotBytes + (uint32_t)h * kResSubBytes +
+                               (uint32_t)row * 128u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float r0, r1, r2, r3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3)
+                       : "r"(rbase + (((uint32_t)i ^ (uint32_t)(row & 7)) * 16u)));
+          f[4 * i] += r0; f[4 * i + 1] += r1; f[4 * i + 2] += r2; f[4 * i + 3] += r3;
+        }
+        if (hh == 2 / SPLIT - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rr->empty_bar + 8u * (uint32_t)rr->idx);
+          if (++rr->idx == rr->slots) { rr->idx = 0; rr->phase ^= 1u; }
+        }
+      } else if (!PLAIN && p.residual_f32 != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 rv = rpre[hh][i >> 2];

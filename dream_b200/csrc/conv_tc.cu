@@ -244,6 +244,19 @@ int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint6
   return 0;
 }
 
+// fp32 tensor, SWIZZLE_128B (inner box = 32 floats = one 128-byte row): residual tiles of conv_tc2.cu.
+int make_tensor_map_f32_sw128(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  DB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  uint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
 // Un-swizzled map over a plain fp32 / uint8 tensor (input staging of first_conv.cu). kind: 0 = fp32, 1 = uint8.
 int make_tensor_map_plain(CUtensorMap* tm, int kind, const void* base, int rank, const uint64_t* dims,
                           const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, const char* what) {

@@ -29,6 +29,8 @@ namespace db200 {
 int make_tensor_map_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estride,
                         const char* what);
+int make_tensor_map_f32_sw128(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes, const uint32_t* box, const char* what);
 int device_sm_count();
 double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, int* th_out);   // conv_tc.cu
 
@@ -46,7 +48,8 @@ struct PhaseMaps {
 template <int kT2N, bool PLAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ PhaseMaps pm,
-                const __grid_constant__ CUtensorMap tmP, const __grid_constant__ ConvParams p) {
+                const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ ConvParams p) {
   constexpr int kT2BHalf = (kT2N / 2) * 128;               // this CTA's half of a weight tile: N/2 rows x 128 B
   constexpr int kT2StageBytes = kABytes + kT2BHalf;        // 32 KB (N = 256) / 24 KB (N = 128)
   constexpr int kTmemCols = 2 * kT2N;                      // two accumulator stages
@@ -60,14 +63,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t smem_out = smem_ab + stages * kT2StageBytes;
   const uint32_t out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
   const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
-  const uint32_t bar_base = smem_out + out_bytes;
+  // fp32 residual ring (ResNet identity stream, non-PLAIN launches only): see the producer loop below
+  const int res_slots = PLAIN ? 0 : p.res_slots;
+  const uint32_t smem_res = smem_out + out_bytes;
+  const uint32_t bar_base = smem_res + (uint32_t)res_slots * kResSlotBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * stages + 4);
+  auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + 6 + s); };
+  auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 6 + 8 + s); };      // res_slots <= 8
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-  const uint32_t smem_bias = bar_base + 256u;
+  const uint32_t smem_bias = bar_base + 512u;
   float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
   stage_bias(p, smem_bias_gen, kT2N);
 
@@ -83,6 +91,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (p.pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kT2Split); }
+    if (res_slots > 0) {
+      tma_prefetch_desc(&tmR);
+      for (int s = 0; s < res_slots; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4 * kT2Split); }
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_ptr_smem);
@@ -112,6 +124,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== TMA producer (both CTAs; bytes are counted on the leader's barriers) =====================
     int stage = 0;
     uint32_t phase = 0;
+    int rs = 0;
+    uint32_t rph = 0;
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
       int sp, n, tx, ty, b;                                   // sp = sub-pixel phase of a phase group (0 otherwise)
       decode(q, sp, n, tx, ty, b);
@@ -129,6 +143,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_load_3d_2sm(sa + kABytes, tmB, bar, kc * 64, n * kT2N + (int)rank * (kT2N / 2), tap);
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (res_slots > 0) {
+        // The identity stream of a ResNet expansion layer: 4 bytes read per output element against 2 * Cin MACs.
+        // Read by the epilogue threads themselves it was latency-bound -- 32 KB in flight per SM, 2.8 TB/s over the
+        // chip.  Here this tile's residual (own CTA's M-tile, own barriers: no pair traffic) is fetched by TMA one
+        // 64-column chunk per slot, a whole tile (res_slots x 32 KB) ahead of the epilogue.
+        for (int c = 0; c < kT2N / 64; ++c) {
+          mbar_wait(rempty_bar(rs), rph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(rfull_bar(rs), (uint32_t)(2 * p.tw * p.th * 128));
+            const uint32_t dst = smem_res + (uint32_t)rs * kResSlotBytes;
+            tma_load_4d(dst, &tmR, rfull_bar(rs), n * kT2N + c * 64, tx * p.tw, ty * p.th, b);
+            tma_load_4d(dst + kResSubBytes, &tmR, rfull_bar(rs), n * kT2N + c * 64 + 32, tx * p.tw, ty * p.th, b);
+          }
+          if (++rs == res_slots) { rs = 0; rph ^= 1u; }
         }
       }
     }
@@ -175,6 +205,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
     float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    ResRing ring;
+    ring.smem = smem_res; ring.full_bar = rfull_bar(0); ring.empty_bar = rempty_bar(0); ring.slots = res_slots;
+    ring.idx = 0; ring.phase = 0;
     const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
       int sp, n, tx, ty, b;
@@ -186,7 +219,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * kT2N);
       epilogue_nhwc_tile<kT2N, kT2Split, true, PLAIN>(p, &pm.c[sp], &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                       as ? tempty_l1 : tempty_l0, n, tx, ty, b, ox, oy, valid, row, lane,
-                                                      epi_tid, chunk_ctr, hsel, csum);
+                                                      epi_tid, chunk_ctr, hsel, csum, nullptr,
+                                                      res_slots > 0 ? &ring : nullptr);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -253,17 +287,36 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
   p.cout_real = d->cout_real;
 
   const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
-  const int budget = 232448 - 1024 - out_bytes - 256 - kT2N * 4;
+  // fp32 residual staged through shared memory (one tile = N / 64 chunk slots ahead) when the identity tensor is a
+  // plain contiguous [B, Ho, Wo, Cout_pad] fp32 tensor and two operand stages still fit next to the ring
+  int res_slots = 0;
+  {
+    const char* e = getenv("DREAMB200_RES_TMA");
+    const bool on = !(e && e[0] == '0');
+    if (on && d->residual_f32 != nullptr && n_phases == 1 && !p.pool && ((uintptr_t)d->residual_f32 & 15) == 0 &&
+        232448 - 1024 - out_bytes - 512 - kT2N * 4 - (kT2N / 64) * (int)kResSlotBytes >= 2 * kT2StageBytes)
+      res_slots = kT2N / 64;
+  }
+  p.res_slots = res_slots;
+  const int budget = 232448 - 1024 - out_bytes - 512 - kT2N * 4 - res_slots * (int)kResSlotBytes;
   int stages = budget / kT2StageBytes;
   if (stages > 8) stages = 8;
   DB_REQUIRE(stages >= 2, "conv_tc2: not enough shared memory for 2 stages");
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * kT2StageBytes + out_bytes + 256 + kT2N * 4;
+  const int smem_bytes = 1024 + stages * kT2StageBytes + out_bytes + res_slots * (int)kResSlotBytes + 512 + kT2N * 4;
 
-  CUtensorMap tmA, tmP;
+  CUtensorMap tmA, tmP, tmR;
   PhaseMaps pm;
   memset(&pm, 0, sizeof(pm));
   memset(&tmP, 0, sizeof(tmP));
+  memset(&tmR, 0, sizeof(tmR));
+  if (res_slots > 0) {
+    const uint64_t C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {C * 4, (uint64_t)d->Wo * C * 4, (uint64_t)d->Ho * d->Wo * C * 4};
+    uint32_t box[4] = {32, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    if (make_tensor_map_f32_sw128(&tmR, d->residual_f32, 4, dims, str, box, "tc2 fp32 residual")) return -1;
+  }
   const uint32_t es4[4] = {1, 1, 1, 1};
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
@@ -307,7 +360,7 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
   }
   const int sms = device_sm_count() & ~1;
   const int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
-  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, p);
+  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, tmR, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -174,6 +174,8 @@ CONV_CASES = {   # name: (B, H, W, Cin, Cout, kind)
     "128_256_100_pool": (2, 100, 100, 128, 256, "pool"),
     "256_512_26x30_s2": (2, 26, 30, 256, 512, "s2"),
     "256_1024_25_1x1res": (2, 25, 25, 256, 1024, "1x1res"),
+    "64_256_100_1x1res": (3, 100, 100, 64, 256, "1x1res"),
+    "512_2048_13_1x1res": (5, 13, 13, 512, 2048, "1x1res"),
     "512_512_25_odd_tiles": (1, 25, 25, 512, 512, "3x3"),
 }
 
@@ -211,11 +213,13 @@ def test_conv_pair_kernel_is_bit_identical_to_single_cta(name, built_lib):
 
     with env(DREAMB200_TC2="0"):
         single = run()
-    with env(DREAMB200_TC2="1"):
+    with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="0"):
         pair = run()
-    assert len(single) == len(pair)
-    for a, b in zip(single, pair):
-        assert torch.equal(a, b)
+    with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="1"):      # fp32 residual staged by TMA (default) vs per-thread loads
+        pair_tma = run()
+    assert len(single) == len(pair) == len(pair_tma)
+    for a, b, c in zip(single, pair, pair_tma):
+        assert torch.equal(a, b) and torch.equal(a, c)
     # ... and both are the convolution (fp32 torch reference of the same fp16 operands)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
