@@ -239,7 +239,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t accph = 0;
     uint32_t chunk_ctr = 0;
-    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float csum[kCsumSize<BLOCK_N, kRsEpiSplit>];
+#pragma unroll
+    for (int i = 0; i < kCsumSize<BLOCK_N, kRsEpiSplit>; ++i) csum[i] = 0.0f;
     float breg[32];
     const bool bias_regs = BLOCK_N == 64 && p.n_tiles == 1 && p.bias != nullptr;
 #pragma unroll

@@ -159,7 +159,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
-    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float csum[kCsumSize<BLOCK_N, kTcSplit>];
+#pragma unroll
+    for (int i = 0; i < kCsumSize<BLOCK_N, kTcSplit>; ++i) csum[i] = 0.0f;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, tx, ty, b;
       decode_tile(p, tile, n, tx, ty, b);

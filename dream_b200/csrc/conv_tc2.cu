@@ -204,7 +204,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
-    float csum[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float csum[kCsumSize<kT2N, kT2Split>];
+#pragma unroll
+    for (int i = 0; i < kCsumSize<kT2N, kT2Split>; ++i) csum[i] = 0.0f;
     ResRing ring;
     ring.smem = smem_res; ring.full_bar = rfull_bar(0); ring.empty_bar = rempty_bar(0); ring.slots = res_slots;
     ring.idx = 0; ring.phase = 0;

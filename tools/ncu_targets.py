@@ -38,6 +38,15 @@ elif target == "wgrad256":
     dy = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
     for _ in range(3):
         ops.wgrad(dy, x, ops.TAPS_3x3)
+elif target == "expand":           # resnet layer3 conv3: 1x1 256 -> 1024 @25x25 + fp32 identity in / out (conv_tc2, residual ring)
+    Bx = 64
+    x = (torch.randn((Bx, 25, 25, 256), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((1024, 256, 1, 1), device="cuda", generator=g) * (1.0 / 256 ** 0.5)
+    wp, bp = ops.pack_conv_weight(w, [(0, 0)]), ops.pad_bias(None, 1024, "cuda")
+    res = torch.randn((Bx, 25, 25, 1024), device="cuda", generator=g)
+    y32 = torch.empty_like(res)
+    for _ in range(3):
+        ops.conv_taps(x, wp, bp, [(0, 0)], 25, 25, relu=True, residual_f32=res, y_f32=y32)
 elif target == "peaks":            # peak extraction on B*7 belief maps of 100x100 (peaks_fused_kernel)
     from dream_b200 import image_proc
     maps = torch.randn((B * 7, 100, 100), device="cuda", generator=g) * 0.2
