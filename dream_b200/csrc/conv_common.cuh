@@ -36,6 +36,7 @@ struct ConvParams {
   int phases, tiles_per_phase;
   unsigned long long mg_phase;
   int res_slots;    // conv_tc2: > 0 = the fp32 residual is staged through a shared-memory ring of this many chunk slots
+  int res_inplace;  // ... and the fp32 output leaves through the same slots (TMA stores)
 };
 
 __host__ __device__ inline unsigned long long div_magic(int d) { return (1ull << 40) / (unsigned long long)d + 1ull; }
@@ -73,6 +74,12 @@ struct ResRing {
   int slots;
   int idx;
   uint32_t phase;
+  // in-place output (y_tm != nullptr): the fp32 result of a chunk is written back over its residual in the slot and
+  // leaves through TMA stores issued with the chunk's fp16 store; the slot returns to the producer only when that
+  // bulk group has been read (one arrival, by the thread that issues the stores), two chunks later.
+  const CUtensorMap* y_tm;
+  int rel_idx;            // next slot to release
+  int pending;            // chunks whose stores have been issued but whose slots are not released yet
 };
 constexpr uint32_t kResSubBytes = 128 * 128;            // one sub-tile: 128 rows x 32 fp32
 constexpr uint32_t kResSlotBytes = 2 * kResSubBytes;
@@ -284,7 +291,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                        : "r"(rbase + (((uint32_t)i ^ (uint32_t)(row & 7)) * 16u)));
           f[4 * i] += r0; f[4 * i + 1] += r1; f[4 * i + 2] += r2; f[4 * i + 3] += r3;
         }
-        if (hh == 2 / SPLIT - 1) {
+        if (hh == 2 / SPLIT - 1 && rr->y_tm == nullptr) {
           __syncwarp();
           if (lane == 0) mbar_arrive(rr->empty_bar + 8u * (uint32_t)rr->idx);
           if (++rr->idx == rr->slots) { rr->idx = 0; rr->phase ^= 1u; }
@@ -319,7 +326,18 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] *= out_scale;
       }
-      if (!PLAIN && y32_row != nullptr) {
+      if (!PLAIN && rr != nullptr && rr->y_tm != nullptr) {
+        // fp32 copy of the output: back into this thread's own 8 pieces of the residual slot (read above), stored by
+        // TMA below.  (Per-thread STG.128s -- 32 rows x 16 bytes per instruction -- back-pressured the whole epilogue:
+        // ncu showed it waiting on the store queue to release the source registers.)
+        const uint32_t rbase = rr->smem + (uint32_t)rr->idx * kResSlotBytes + (uint32_t)h * kResSubBytes +
+                               (uint32_t)row * 128u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((uint32_t)i ^ (uint32_t)(row & 7)) * 16u)),
+                       "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
+                       : "memory");
+      } else if (!PLAIN && y32_row != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(y32_row + c * 64 + h * 32 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -399,6 +417,18 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     if (epi_tid < 32) {                                // stores that used obuf / pbuf two chunks ago have read them
       if (elect_one()) {
         if (p.pool && p.store_full) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+        if constexpr (!PLAIN) {
+          if (rr != nullptr && rr->y_tm != nullptr && rr->pending == 2) {
+            // ... and so has the fp32 store of the chunk two back: its slot goes back to the producer
+            mbar_arrive(rr->empty_bar + 8u * (uint32_t)rr->rel_idx);
+          }
+        }
+      }
+    }
+    if constexpr (!PLAIN) {
+      if (rr != nullptr && rr->y_tm != nullptr && rr->pending == 2) {   // (cursor kept by every thread alike)
+        if (++rr->rel_idx == rr->slots) rr->rel_idx = 0;
+        rr->pending = 1;
       }
     }
     named_bar_sync(1, kEpiThreads);
@@ -442,7 +472,20 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
     if (epi_tid < 32 && (!p.pool || p.store_full)) {
       if (elect_one()) {
         tma_store_4d(tmC, obuf, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
+        if constexpr (!PLAIN) {
+          if (rr != nullptr && rr->y_tm != nullptr) {
+            const uint32_t src = rr->smem + (uint32_t)rr->idx * kResSlotBytes;
+            tma_store_4d(rr->y_tm, src, n * BLOCK_N + c * 64, tx * p.tw, ty * p.th, b);
+            tma_store_4d(rr->y_tm, src + kResSubBytes, n * BLOCK_N + c * 64 + 32, tx * p.tw, ty * p.th, b);
+          }
+        }
         tma_store_commit();
+      }
+    }
+    if constexpr (!PLAIN) {
+      if (rr != nullptr && rr->y_tm != nullptr) {
+        if (++rr->idx == rr->slots) { rr->idx = 0; rr->phase ^= 1u; }
+        ++rr->pending;
       }
     }
     if (p.pool && !shfl_pool) {

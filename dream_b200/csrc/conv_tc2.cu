@@ -49,7 +49,7 @@ template <int kT2N, bool PLAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ PhaseMaps pm,
                 const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmR,
-                const __grid_constant__ ConvParams p) {
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ ConvParams p) {
   constexpr int kT2BHalf = (kT2N / 2) * 128;               // this CTA's half of a weight tile: N/2 rows x 128 B
   constexpr int kT2StageBytes = kABytes + kT2BHalf;        // 32 KB (N = 256) / 24 KB (N = 128)
   constexpr int kTmemCols = 2 * kT2N;                      // two accumulator stages
@@ -93,7 +93,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kT2Split); }
     if (res_slots > 0) {
       tma_prefetch_desc(&tmR);
-      for (int s = 0; s < res_slots; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4 * kT2Split); }
+      // (in-place fp32 output: a slot is released by the one thread that issued its TMA stores, see ResRing)
+      const uint32_t releasers = p.res_inplace ? 1u : (uint32_t)(4 * kT2Split);
+      if (p.res_inplace) tma_prefetch_desc(&tmY);
+      for (int s = 0; s < res_slots; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), releasers); }
     }
     fence_mbar_init();
   }
@@ -210,6 +213,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ResRing ring;
     ring.smem = smem_res; ring.full_bar = rfull_bar(0); ring.empty_bar = rempty_bar(0); ring.slots = res_slots;
     ring.idx = 0; ring.phase = 0;
+    ring.y_tm = (res_slots > 0 && p.res_inplace) ? &tmY : nullptr; ring.rel_idx = 0; ring.pending = 0;
     const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
       int sp, n, tx, ty, b;
@@ -298,26 +302,37 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
     if (on && d->residual_f32 != nullptr && n_phases == 1 && !p.pool && ((uintptr_t)d->residual_f32 & 15) == 0 &&
         232448 - 1024 - out_bytes - 512 - kT2N * 4 - (kT2N / 64) * (int)kResSlotBytes >= 2 * kT2StageBytes)
       res_slots = kT2N / 64;
+    // with an fp32 output too (every expansion layer but a stage's last) the result leaves through the SAME slots: two
+    // of them are then busy with pending stores, so the ring grows by one slot and the operand pipeline -- idle 90 % of
+    // the time in these HBM-bound layers -- shrinks to a single stage
+    const char* e2 = getenv("DREAMB200_RES_INPLACE");
+    if (res_slots > 0 && d->y_f32 != nullptr && ((uintptr_t)d->y_f32 & 15) == 0 && !(e2 && e2[0] == '0') &&
+        232448 - 1024 - out_bytes - 512 - kT2N * 4 - (res_slots + 1) * (int)kResSlotBytes >= kT2StageBytes) {
+      res_slots += 1;
+      p.res_inplace = 1;
+    }
   }
   p.res_slots = res_slots;
   const int budget = 232448 - 1024 - out_bytes - 512 - kT2N * 4 - res_slots * (int)kResSlotBytes;
   int stages = budget / kT2StageBytes;
   if (stages > 8) stages = 8;
-  DB_REQUIRE(stages >= 2, "conv_tc2: not enough shared memory for 2 stages");
+  DB_REQUIRE(stages >= (p.res_inplace ? 1 : 2), "conv_tc2: not enough shared memory for the operand stages");
   p.stages = stages;
   const int smem_bytes = 1024 + stages * kT2StageBytes + out_bytes + res_slots * (int)kResSlotBytes + 512 + kT2N * 4;
 
-  CUtensorMap tmA, tmP, tmR;
+  CUtensorMap tmA, tmP, tmR, tmY;
   PhaseMaps pm;
   memset(&pm, 0, sizeof(pm));
   memset(&tmP, 0, sizeof(tmP));
   memset(&tmR, 0, sizeof(tmR));
+  memset(&tmY, 0, sizeof(tmY));
   if (res_slots > 0) {
     const uint64_t C = (uint64_t)d->Cout_pad;
     uint64_t dims[4] = {C, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
     uint64_t str[3] = {C * 4, (uint64_t)d->Wo * C * 4, (uint64_t)d->Ho * d->Wo * C * 4};
     uint32_t box[4] = {32, (uint32_t)p.tw, (uint32_t)p.th, 1};
     if (make_tensor_map_f32_sw128(&tmR, d->residual_f32, 4, dims, str, box, "tc2 fp32 residual")) return -1;
+    if (p.res_inplace && make_tensor_map_f32_sw128(&tmY, d->y_f32, 4, dims, str, box, "tc2 fp32 output")) return -1;
   }
   const uint32_t es4[4] = {1, 1, 1, 1};
   {
@@ -362,7 +377,7 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
   }
   const int sms = device_sm_count() & ~1;
   const int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
-  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, tmR, p);
+  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, tmR, tmY, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -215,11 +215,13 @@ def test_conv_pair_kernel_is_bit_identical_to_single_cta(name, built_lib):
         single = run()
     with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="0"):
         pair = run()
-    with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="1"):      # fp32 residual staged by TMA (default) vs per-thread loads
+    with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="1", DREAMB200_RES_INPLACE="0"):   # fp32 residual staged by TMA
         pair_tma = run()
-    assert len(single) == len(pair) == len(pair_tma)
-    for a, b, c in zip(single, pair, pair_tma):
-        assert torch.equal(a, b) and torch.equal(a, c)
+    with env(DREAMB200_TC2="1", DREAMB200_RES_TMA="1", DREAMB200_RES_INPLACE="1"):   # ... fp32 output through the same slots (default)
+        pair_inplace = run()
+    assert len(single) == len(pair) == len(pair_tma) == len(pair_inplace)
+    for a, b, c, d in zip(single, pair, pair_tma, pair_inplace):
+        assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d)
     # ... and both are the convolution (fp32 torch reference of the same fp16 operands)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
