@@ -47,6 +47,12 @@ elif target == "expand":           # resnet layer3 conv3: 1x1 256 -> 1024 @25x25
     y32 = torch.empty_like(res)
     for _ in range(3):
         ops.conv_taps(x, wp, bp, [(0, 0)], 25, 25, relu=True, residual_f32=res, y_f32=y32)
+elif target == "peaks208":         # resnet-H shape: 64 x 7 maps of 208x208 (peaks_banded_kernel)
+    from dream_b200 import image_proc
+    maps = torch.randn((64 * 7, 208, 208), device="cuda", generator=g) * 0.2
+    maps[:, 90:94, 120:124] += 1.0
+    for _ in range(3):
+        image_proc.find_peaks_device(maps, 0.4395)
 elif target == "peaks":            # peak extraction on B*7 belief maps of 100x100 (peaks_fused_kernel)
     from dream_b200 import image_proc
     maps = torch.randn((B * 7, 100, 100), device="cuda", generator=g) * 0.2
