@@ -255,6 +255,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="inference steps launched eagerly instead of graph replay")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--layer-table", default=None, help="write per-layer timings (JSON) to this path")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("DREAMB200_BENCH_STREAMS", "1")), choices=[1, 2],
+                    help="inference: 2 = the two captured steps replay on two streams (two batches in flight)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.steps_ref = min(args.steps, 3)
@@ -339,9 +341,17 @@ def measure(args, workload, rank, world, local, dev, primary=True):
     if mode == "infer" and not args.no_graph:
         graphs = [net.capture_inference(x, adopt=True) for x in xs]
 
+    # --streams 2: graph i&1 replays on its own stream, so two batches are in flight and the tail of every kernel
+    # (SMs idle while the last tiles of a persistent grid finish, launch gaps) is filled by the other batch's kernels
+    two = graphs is not None and args.streams == 2
+    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if two else None
+
     def step_device(i):
         if mode == "train":          # fwd + MSE + bwd + gradient all-reduce + Adam step (DreamNetwork.train)
             return net.train([xs[i & 1]], targets[i & 1])
+        if two and ops.PROFILE is None:
+            with torch.cuda.stream(side[i & 1]):
+                return graphs[i & 1]()[1]
         if graphs is not None and ops.PROFILE is None:
             return graphs[i & 1]()[1]
         with torch.no_grad():
@@ -375,11 +385,17 @@ def measure(args, workload, rank, world, local, dev, primary=True):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
+        if two and not whole:
+            for st in side:
+                st.wait_stream(torch.cuda.current_stream(dev))
         if whole:
             fn(steps)
         else:
             for i in range(steps):
                 fn(i)
+        if two and not whole:
+            for st in side:
+                torch.cuda.current_stream(dev).wait_stream(st)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -553,7 +569,8 @@ def measure(args, workload, rank, world, local, dev, primary=True):
             "parity": parity,
             "allreduce": comm,
             "latency_b1": latency,
-            "launch_mode": ("cuda graph replay, %d libdreamb200 kernels per step" % graphs[0].kernels_per_replay)
+            "launch_mode": ("cuda graph replay, %d libdreamb200 kernels per step" % graphs[0].kernels_per_replay +
+                            (", two batches in flight on two streams" if two else ""))
             if graphs is not None else "eager",
         }
         if not primary:

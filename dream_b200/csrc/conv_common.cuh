@@ -84,6 +84,16 @@ struct ResRing {
 constexpr uint32_t kResSubBytes = 128 * 128;            // one sub-tile: 128 rows x 32 fp32
 constexpr uint32_t kResSlotBytes = 2 * kResSubBytes;
 
+// ReLU gate tiles of a data-gradient launch staged in shared memory by a dedicated TMA warp (conv_rs2.cu): a ring of
+// `slots` 64-column chunks (128 rows x 128 B, SWIZZLE_128B -- the layout of the output staging buffer).  Every
+// epilogue warp keeps its own cursor; a slot goes back to the TMA warp once all epilogue warps have read it.
+struct GateRing {
+  uint32_t smem, full_bar, empty_bar;
+  int slots, idx;
+  uint32_t phase;
+};
+constexpr uint32_t kGateSlotBytes = 128 * 128;
+
 // One output tile (128 accumulator rows x BLOCK_N columns) of the NHWC fp16 path; called by the 4 epilogue
 // warps (128 threads, named barrier 1).  `t_row` = TMEM address of this thread's lane quarter / accumulator stage,
 // `smem_bias` = shared-memory copy of the current channel tile's fp32 bias (BLOCK_N floats, zeros when none).
@@ -99,14 +109,16 @@ constexpr uint32_t kResSlotBytes = 2 * kResSubBytes;
 // PLAIN: the launch has no residual / fp32 stream / gate / out_scale / colsum / absmax (every inference layer of the
 // vgg networks): those options compile away -- the epilogue of the 64-channel layers paces the kernel (two warps
 // per scheduler, one dependent chain per tile), so every runtime test on the chain counts.
-template <int BLOCK_N, int SPLIT = 1, bool CLUSTER_ARRIVE = false, bool PLAIN = false>
+// GRING: the ReLU gate always arrives through a GateRing (`gr`), the per-thread gate loads compile away.
+template <int BLOCK_N, int SPLIT = 1, bool CLUSTER_ARRIVE = false, bool PLAIN = false, bool GRING = false>
 __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
                                                    uint32_t smem_bias, float* smem_bias_gen, uint32_t tempty_bar_addr,
                                                    int n, int tx, int ty, int b, int ox, int oy, bool valid, int row,
                                                    int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0,
                                                    float* csum = nullptr, const float* breg = nullptr,
-                                                   ResRing* rr = nullptr) {
+                                                   ResRing* rr = nullptr, uint32_t tfull_addr = 0u,
+                                                   uint32_t tfull_phase = 0u, GateRing* gr = nullptr) {
   constexpr int kEpiThreads = 128 * SPLIT;
   constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
@@ -148,6 +160,29 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
   };
   if constexpr (!PLAIN) {
     if (p.residual_f32 != nullptr && rr == nullptr) prefetch_res32(0);
+  }
+  // ReLU gate of a data-gradient launch (the forward output of the layer below, long evicted from L2): one HBM round
+  // trip per chunk when it is read after the TMEM load -- the gated 64-channel data gradients ran at half the speed of
+  // the same convolution forward.  The gate does not depend on the accumulator, so chunk 0's values are requested
+  // BEFORE the wait for the tile's MMAs (`tfull_addr`, when the caller delegates that wait) and chunk c+1's while
+  // chunk c is finished.
+  uint4 gpre[2 / SPLIT][4];
+  auto prefetch_gate = [&](int c) {
+#pragma unroll
+    for (int hh = 0; hh < 2 / SPLIT; ++hh) {
+      const int h = SPLIT == 2 ? hsel : hh;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        gpre[hh][i] = gate_row != nullptr ? __ldg(reinterpret_cast<const uint4*>(gate_row + c * 64 + h * 32) + i)
+                                          : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  if constexpr (!PLAIN && !GRING) {
+    if (p.gate != nullptr && gr == nullptr) prefetch_gate(0);
+  }
+  if (tfull_addr != 0u) {
+    mbar_wait(tfull_addr, tfull_phase);
+    tc_fence_after();
   }
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N / 64; ++c, ++chunk_ctr) {
@@ -310,10 +345,20 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
       }
       if (!PLAIN && p.gate != nullptr) {
         // data gradient leaving through the previous layer's ReLU: keep it where that layer's output was > 0
+        if ((GRING || gr != nullptr) && hh == 0) mbar_wait(gr->full_bar + 8u * (uint32_t)gr->idx, gr->phase);
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 gv = make_uint4(0u, 0u, 0u, 0u);
-          if (gate_row != nullptr) gv = __ldg(reinterpret_cast<const uint4*>(gate_row + c * 64 + h * 32 + i));
+          uint4 gv;
+          if (GRING || gr != nullptr) {
+            // staged tile: this thread's row, 16-byte piece h * 4 + i / 8 (swizzled like the output staging buffer);
+            // rows outside the image were zero-filled by the TMA, i.e. gated off like `gate_row == nullptr`
+            const uint32_t src = gr->smem + (uint32_t)gr->idx * kGateSlotBytes + (uint32_t)row * 128u +
+                                 ((((uint32_t)h * 4u + (uint32_t)(i >> 3)) ^ (uint32_t)(row & 7)) * 16u);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(gv.x), "=r"(gv.y), "=r"(gv.z), "=r"(gv.w) : "r"(src) : "memory");
+          } else {
+            gv = gpre[hh][i >> 3];
+          }
           const __half2* gh = reinterpret_cast<const __half2*>(&gv);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -321,6 +366,15 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
             f[i + 2 * j] = gf.x > 0.0f ? f[i + 2 * j] * out_scale : 0.0f;
             f[i + 2 * j + 1] = gf.y > 0.0f ? f[i + 2 * j + 1] * out_scale : 0.0f;
           }
+        }
+        if (GRING || gr != nullptr) {
+          if (hh == 2 / SPLIT - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gr->empty_bar + 8u * (uint32_t)gr->idx);
+            if (++gr->idx == gr->slots) { gr->idx = 0; gr->phase ^= 1u; }
+          }
+        } else if (!GRING && hh == 2 / SPLIT - 1 && c + 1 < BLOCK_N / 64) {
+          prefetch_gate(c + 1);
         }
       } else if (!PLAIN && p.out_scale != nullptr) {
 #pragma unroll

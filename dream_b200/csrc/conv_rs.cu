@@ -243,15 +243,15 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < kCsumSize<BLOCK_N, kRsEpiSplit>; ++i) csum[i] = 0.0f;
     float breg[32];
-    const bool bias_regs = BLOCK_N == 64 && p.n_tiles == 1 && p.bias != nullptr;
+    const bool bias_regs = PLAIN && BLOCK_N == 64 && p.n_tiles == 1 && p.bias != nullptr;
 #pragma unroll
     for (int i = 0; i < 32; ++i) breg[i] = bias_regs ? __ldg(p.bias + hsel * 32 + i) : 0.0f;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, tx, ty, b;
       decode_tile(p, tile, n, tx, ty, b);
-      mbar_wait(tfull_bar(acc), accph);
-      tc_fence_after();
       if constexpr (HEAD) {
+        mbar_wait(tfull_bar(acc), accph);
+        tc_fence_after();
         // fp32 NCHW head: this warp's 8 of the 16 accumulator columns (hsel), channels < cout_real are real
         const int ox = tx * kRsTw + lx, oy = ty * kRsTh + ly;
         uint32_t v[8];
@@ -286,7 +286,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * SUBTILES + sub) * BLOCK_N);
         epilogue_nhwc_tile<BLOCK_N, kRsEpiSplit, false, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                  tempty_bar(acc), n, tx, tys, b, ox, oy, valid, row, lane, epi_tid,
-                                                 chunk_ctr, hsel, csum, bias_regs ? breg : nullptr);
+                                                 chunk_ctr, hsel, csum, bias_regs ? breg : nullptr, nullptr,
+                                                 sub == 0 ? tfull_bar(acc) : 0u, accph);   // (sub-tile 0 waits for the MMAs)
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1u;

@@ -32,6 +32,8 @@ int device_sm_count();
 constexpr int kR2Tw = 8, kR2Th = 16;
 constexpr int kR2EpiSplit = 2;
 constexpr int kR2Threads = 64 + 128 * kR2EpiSplit;
+constexpr int kR2ThreadsGate = kR2Threads + 32;                          // + the gate TMA warp (gated launches only)
+constexpr int kR2GateSlots = 4;                                          // 64-column gate chunks in flight per CTA (max)
 constexpr int kR2Rows = kR2Th + 2;                                       // image rows per slab
 constexpr int kR2Pitch = 1280;                                           // 10 pixels x 128 B
 constexpr int kR2SlabTx = kR2Rows * kR2Pitch;
@@ -39,6 +41,7 @@ constexpr int kR2SlabBytes = ((kR2SlabTx + 1023) / 1024) * 1024;
 
 struct Rs2Extra {
   int sa, sb;        // ring depths: activation slabs, weight half-tiles (streamed mode)
+  int gate_slots;    // > 0: the ReLU gate is staged through shared memory by warp 10 (kR2ThreadsGate threads)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo2(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -52,10 +55,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo2(uint32_t smem_addr, u
 }
 
 template <int BLOCK_N, bool RESIDENT, bool PLAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kR2Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kR2ThreadsGate, 1)
 conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
-                const __grid_constant__ ConvParams p, const __grid_constant__ Rs2Extra x) {
+                const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams p,
+                const __grid_constant__ Rs2Extra x) {
   constexpr int kBHalf = (BLOCK_N / 2) * 128;                            // this CTA's half of a weight tile
   constexpr int kTmemCols = 2 * BLOCK_N;                                 // 128 or 256
   constexpr uint32_t kIdesc = umma_idesc_f16_m256(BLOCK_N);
@@ -69,7 +73,9 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t smem_b = smem_a + sa * kR2SlabBytes;
   const uint32_t smem_out = smem_b + (RESIDENT ? n_wtiles : 3 * sb) * kBHalf;      // sb counts GROUPS of 3 tiles
   const uint32_t smem_pool = smem_out + 2 * kStageOutBytes;
-  const uint32_t bar_base = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
+  const int gate_slots = PLAIN ? 0 : x.gate_slots;
+  const uint32_t smem_gate = smem_pool + (p.pool ? 2 * kPoolBytes : 0);
+  const uint32_t bar_base = smem_gate + (uint32_t)gate_slots * kGateSlotBytes;
   auto afull = [&](int s) { return bar_base + 8u * s; };
   auto aempty = [&](int s) { return bar_base + 8u * (sa + s); };
   auto bfull = [&](int s) { return bar_base + 8u * (2 * sa + s); };
@@ -79,8 +85,10 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tempty_bar = [&](int a) { return misc + 16u + 8u * a; };
   const uint32_t wbar = misc + 32u;
   const uint32_t tmem_ptr_smem = misc + 40u;
+  auto gfull = [&](int s) { return misc + 64u + 8u * s; };               // kR2GateSlots <= 4
+  auto gempty = [&](int s) { return misc + 96u + 8u * s; };
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-  const uint32_t smem_bias = misc + 64u;
+  const uint32_t smem_bias = misc + 128u;
   float* smem_bias_gen = reinterpret_cast<float*>(smem_gen + (smem_bias - smem_base));
   stage_bias(p, smem_bias_gen, BLOCK_N);
 
@@ -96,6 +104,8 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < sb; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * kR2EpiSplit); }
     mbar_init(wbar, 1);
+    for (int s = 0; s < gate_slots; ++s) { mbar_init(gfull(s), 1); mbar_init(gempty(s), 4 * kR2EpiSplit); }
+    if (gate_slots > 0) tma_prefetch_desc(&tmG);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_ptr_smem);
@@ -213,6 +223,31 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     __syncwarp();
+  } else if (warp == 10) {
+    // ===================== ReLU-gate TMA (data-gradient launches) =====================
+    // The gate is the forward output of the layer below: 128 B per pixel, long evicted from L2.  Read per thread (one
+    // row each, rows 128 B apart) every warp-level load touches 32 cache lines: 1024 L1 wavefronts per tile -- on the
+    // pipe the tensor core's operand reads already fill to 80 %; the gated 64 -> 64 data gradient ran at 3.1 ms against
+    // 1.6 ms forward.  Staged by TMA (128 wavefronts written + 128 read per tile) the tile costs a quarter of that,
+    // and the loads run `gate_slots` chunks ahead of the epilogue.
+    if (gate_slots > 0) {
+      int gs = 0;
+      uint32_t gph = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+        int n, tx, typ, b;
+        decode_tile(p, tile, n, tx, typ, b);
+        const int x0 = tx * kR2Tw, y0 = (typ * 2 + (int)rank) * kR2Th;
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          mbar_wait(gempty(gs), gph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(gfull(gs), kGateSlotBytes);
+            tma_load_4d(smem_gate + (uint32_t)gs * kGateSlotBytes, &tmG, gfull(gs), c * 64, x0, y0, b);
+          }
+          if (++gs == gate_slots) { gs = 0; gph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue (both CTAs drain their own TMEM half) =====================
     const int q = warp & 3;
@@ -227,22 +262,25 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
     for (int i = 0; i < kCsumSize<BLOCK_N, kR2EpiSplit>; ++i) csum[i] = 0.0f;
     float breg[32];
-    const bool bias_regs = BLOCK_N == 64 && p.bias != nullptr;
+    const bool bias_regs = PLAIN && BLOCK_N == 64 && p.bias != nullptr;   // (!PLAIN: registers go to csum / gate)
 #pragma unroll
     for (int i = 0; i < 32; ++i) breg[i] = bias_regs ? __ldg(p.bias + hsel * 32 + i) : 0.0f;
     const uint32_t tempty_l0 = mapa_cluster(tempty_bar(0), 0), tempty_l1 = mapa_cluster(tempty_bar(1), 0);
+    GateRing gring;
+    gring.smem = smem_gate; gring.full_bar = gfull(0); gring.empty_bar = gempty(0); gring.slots = gate_slots;
+    gring.idx = 0; gring.phase = 0;
     for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
       int n, tx, typ, b;
       decode_tile(p, tile, n, tx, typ, b);
       const int ty = typ * 2 + (int)rank;
-      mbar_wait(tfull_bar(acc), accph);
-      tc_fence_after();
       const int ox = tx * kR2Tw + lx, oy = ty * kR2Th + ly;
       const bool valid = (ox < p.Wo) && (oy < p.Ho);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      epilogue_nhwc_tile<BLOCK_N, kR2EpiSplit, true, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
+      epilogue_nhwc_tile<BLOCK_N, kR2EpiSplit, true, PLAIN, true>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                      acc ? tempty_l1 : tempty_l0, 0, tx, ty, b, ox, oy, valid, row, lane,
-                                                     epi_tid, chunk_ctr, hsel, csum, bias_regs ? breg : nullptr);
+                                                     epi_tid, chunk_ctr, hsel, csum, bias_regs ? breg : nullptr, nullptr,
+                                                     tfull_bar(acc), accph,     // (waits for the tile's MMAs itself)
+                                                     &gring);                   // (gated launches always stage the gate)
       acc ^= 1;
       if (acc == 0) accph ^= 1u;
     }
@@ -261,7 +299,7 @@ conv_rs2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int BLOCK_N, bool RESIDENT>
-static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
+static int launch_rs2(const dreamb200_conv_desc* d, int gate_slots, cudaStream_t stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.tw = kR2Tw; p.th = kR2Th;
@@ -294,7 +332,9 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   constexpr int kBHalf = (BLOCK_N / 2) * 128;
   const int out_bytes = 2 * kStageOutBytes + (p.pool ? 2 * kPoolBytes : 0);
   Rs2Extra x;
-  int budget = 232448 - 1024 - out_bytes - 1024 - BLOCK_N * 4;
+  x.gate_slots = gate_slots;
+  const int gate_bytes = gate_slots * (int)kGateSlotBytes;
+  int budget = 232448 - 1024 - out_bytes - gate_bytes - 1024 - BLOCK_N * 4;
   if (RESIDENT) {
     budget -= 9 * p.kchunks * kBHalf;
     x.sa = budget / kR2SlabBytes;
@@ -307,11 +347,13 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   }
   DB_REQUIRE(x.sa >= 2 && x.sb >= 1 && (RESIDENT || x.sb >= 2), "conv_rs2: shared memory budget too small");
   const int smem_bytes =
-      1024 + x.sa * kR2SlabBytes + (RESIDENT ? 9 * p.kchunks : 3 * x.sb) * kBHalf + out_bytes + 1024 + BLOCK_N * 4;
+      1024 + x.sa * kR2SlabBytes + (RESIDENT ? 9 * p.kchunks : 3 * x.sb) * kBHalf + out_bytes + gate_bytes + 1024 +
+      BLOCK_N * 4;
 
-  CUtensorMap tmA, tmB, tmC, tmP;
+  CUtensorMap tmA, tmB, tmC, tmP, tmG;
   memset(&tmC, 0, sizeof(tmC));
   memset(&tmP, 0, sizeof(tmP));
+  memset(&tmG, 0, sizeof(tmG));
   const uint32_t es4[4] = {1, 1, 1, 1};
   {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
@@ -339,6 +381,14 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
     uint32_t box[4] = {64, kR2Tw, kR2Th, 1};
     if (make_tensor_map_f16(&tmC, d->y, 4, dims, str, box, es4, "rs2 output")) return -1;
   }
+  if (gate_slots > 0) {
+    // the gate has the output's geometry, densely packed NHWC
+    const uint64_t C = (uint64_t)d->Cout_pad;
+    uint64_t dims[4] = {C, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->B};
+    uint64_t str[3] = {C * 2, (uint64_t)d->Wo * C * 2, (uint64_t)d->Ho * d->Wo * C * 2};
+    uint32_t box[4] = {64, kR2Tw, kR2Th, 1};
+    if (make_tensor_map_f16(&tmG, d->gate, 4, dims, str, box, es4, "rs2 gate")) return -1;
+  }
   const bool plain = d->residual == nullptr && d->residual_f32 == nullptr && d->y_f32 == nullptr &&
                      d->gate == nullptr && d->out_scale == nullptr && d->colsum == nullptr && d->absmax == nullptr;
   auto kern = plain ? conv_rs2_kernel<BLOCK_N, RESIDENT, true> : conv_rs2_kernel<BLOCK_N, RESIDENT, false>;
@@ -349,7 +399,7 @@ static int launch_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   }
   const int sms = device_sm_count() & ~1;
   int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
-  kern<<<grid, kR2Threads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, p, x);
+  kern<<<grid, gate_slots > 0 ? kR2ThreadsGate : kR2Threads, smem_bytes, stream>>>(tmA, tmB, tmC, tmP, tmG, p, x);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -383,18 +433,29 @@ int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream) {
   }
   if (util < min_util) return 0;
   const int kchunks = d->Cin / 64;
+  // ReLU gate of a data-gradient launch: staged through shared memory by TMA (DREAMB200_GATE_TMA=0: per-thread loads)
+  static int gate_tma = -1;
+  if (gate_tma < 0) {
+    const char* e = getenv("DREAMB200_GATE_TMA");
+    gate_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (d->gate != nullptr && (!gate_tma || ((uintptr_t)d->gate & 15) != 0)) return 0;     // -> conv_rs / conv_tc
+  // 64 output channels: short tiles (36 MMAs), four chunks = four tiles ahead; 128: a tile is >= 72 64-cycle MMAs and
+  // its two chunks free their slots early in the epilogue -- two slots are enough and leave the weight ring its depth
+  // (with four, 256 -> 128 @100x100 went 1.27 -> 1.45 ms)
+  const int gate_slots = d->gate != nullptr ? (d->Cout_pad == 64 ? kR2GateSlots : 2) : 0;
   // resident half tiles need room for at least two activation slabs next to them
-  const int out_bytes = 2 * kStageOutBytes + (d->y_pool != nullptr ? 2 * kPoolBytes : 0);
+  const int out_bytes = 2 * kStageOutBytes + (d->y_pool != nullptr ? 2 * kPoolBytes : 0) + gate_slots * (int)kGateSlotBytes;
   const int resident_bytes = 9 * kchunks * (d->Cout_pad / 2) * 128;
   const bool resident = 232448 - 1024 - out_bytes - 1024 - d->Cout_pad * 4 - resident_bytes >= 2 * kR2SlabBytes;
   int rc;
   if (d->Cout_pad == 64) {
     if (kchunks == 1 && !(mode & 1)) return 0;
     if (kchunks > 1 && !(mode & 4)) return 0;
-    rc = resident ? launch_rs2<64, true>(d, stream) : launch_rs2<64, false>(d, stream);
+    rc = resident ? launch_rs2<64, true>(d, gate_slots, stream) : launch_rs2<64, false>(d, gate_slots, stream);
   } else {
     if (kchunks == 1 ? !(mode & 8) : !(mode & 2)) return 0;
-    rc = resident ? launch_rs2<128, true>(d, stream) : launch_rs2<128, false>(d, stream);
+    rc = resident ? launch_rs2<128, true>(d, gate_slots, stream) : launch_rs2<128, false>(d, gate_slots, stream);
   }
   return rc == 0 ? 1 : rc;
 }

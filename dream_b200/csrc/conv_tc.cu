@@ -167,15 +167,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode_tile(p, tile, n, tx, ty, b);
       const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
       const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho);
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
       if constexpr (OUT_MODE == DREAMB200_OUT_NHWC_F16) {
         epilogue_nhwc_tile<BLOCK_N, kTcSplit, false, PLAIN>(p, &tmC, &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                               tempty_bar(as), n, tx, ty, b, ox, oy, valid, row, lane, epi_tid,
-                                              chunk_ctr, hsel, csum);
+                                              chunk_ctr, hsel, csum, nullptr, nullptr, tfull_bar(as), aphase);
       } else {
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
         // fp32 NCHW head: BLOCK_N == 16 accumulator columns, first cout_real are real channels
         uint32_t v[16];
         tmem_ld_32x32b_x16(t_row, v);

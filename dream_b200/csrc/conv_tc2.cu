@@ -220,13 +220,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       decode(q, sp, n, tx, ty, b);
       const int ox = tx * p.tw + lx, oy = ty * p.th + ly;
       const bool valid = (ly < p.th) && (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * kT2N);
       epilogue_nhwc_tile<kT2N, kT2Split, true, PLAIN>(p, &pm.c[sp], &tmP, t_row, smem_out, smem_pool, smem_bias, smem_bias_gen,
                                                       as ? tempty_l1 : tempty_l0, n, tx, ty, b, ox, oy, valid, row, lane,
                                                       epi_tid, chunk_ctr, hsel, csum, nullptr,
-                                                      res_slots > 0 ? &ring : nullptr);
+                                                      res_slots > 0 ? &ring : nullptr, tfull_bar(as), aphase);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }

@@ -1,7 +1,6 @@
 // wgrad_pair.cu -- CTA-pair (tcgen05 cta_group::2) variant of the row-shared 3x3 weight-gradient kernel
 // (wgrad3x3_kernel<128> in train_kernels.cu) for layers with Cout % 256 == 0 and Cin % 128 == 0.
-// OPT-IN (DREAMB200_WGRAD3_2SM=1) and NOT YET VALIDATED ON A GPU: written at the end of round 1 after the GPU budget
-// was spent; tools/wgrad_pair_check.py is its bring-up harness.
+// On by default since round 2 (tools/wgrad_pair_check.py, tests/test_gpu_kernel_variants.py).
 //
 // Why: dW[tap][co][ci] = sum_px dY[px][co] * X[px + tap][ci] runs as M = 128 (co) x N = 128 (ci) MMAs with K = 16 pixels,
 // both operands MN-major from shared memory: 32 + 32 operand wavefronts per 64-cycle MMA -- exactly the shared-memory
@@ -11,6 +10,12 @@
 // Each CTA's TMEM half holds its co tile x all 128 ci for the three taps of the kernel row; the epilogue is unchanged.
 // Pair protocol as in conv_rs2.cu (bytes counted on the leader's full barrier, multicast commits); the accumulators
 // are drained once, after the split's last k-block, so there is no accumulator hand-back.
+//
+// Tile height.  A k-block is an 8-pixel-wide (one swizzle atom per image row), `th`-row tile of the map; pixels
+// outside the image are TMA zero fill, i.e. MMAs spent on zeros.  With the fixed 16 rows of round 1 a 50x50 map was cut
+// into 7 x 4 tiles = 3584 pixel slots for 2500 pixels (70 % useful, 1.19 PFLOP/s on the 512-channel layers against 1.40 at
+// 100x100).  `th` is now chosen per launch (any even number up to 26; it only enters the TMA boxes, the stage layout
+// and the MMA loop bound): 10 rows for 50x50 (89 %), 20 for 100x100 (96 %), 26 for 25x25 (75 %, was 61 %).
 #include "common.cuh"
 #include "dreamb200.h"
 
@@ -31,15 +36,17 @@ struct WgradPairParams {
   float* dw;
   int Cout_pad, Cin_pad;
   int stages;
+  int th;            // image rows per k-block (even)
 };
 
 constexpr int kWpThreads = 192;
-constexpr int kWpChunk = 128 * 128;            // [128 px][64 ch] fp16
-constexpr int kWpSlab = 16 * 1280;             // 16 image rows x 10 pixels x 128 B
-constexpr int kWpABytes = 2 * kWpChunk;        // dY: 128 px x (2 x 64) co of this CTA's co tile
-constexpr int kWpBBytes = kWpSlab;             // X: this CTA's 64 of the ci tile's 128 channels
-constexpr int kWpStageBytes = kWpABytes + kWpBBytes;
 constexpr int kWpN = 128;
+// one pipeline stage for `th` image rows: dY = 2 chunks of [8 * th px][64 co] (this CTA's co tile), X = a slab of th
+// image rows x 10 pixels x 64 ci (this CTA's half of the ci tile), padded to the 1024-byte swizzle period
+__host__ __device__ constexpr uint32_t wp_chunk_bytes(int th) { return (uint32_t)th * 1024u; }
+__host__ __device__ constexpr uint32_t wp_slab_tx(int th) { return (uint32_t)th * 1280u; }
+__host__ __device__ constexpr uint32_t wp_slab_bytes(int th) { return (wp_slab_tx(th) + 1023u) & ~1023u; }
+__host__ __device__ constexpr uint32_t wp_stage_bytes(int th) { return 2u * wp_chunk_bytes(th) + wp_slab_bytes(th); }
 
 __host__ __device__ constexpr uint32_t umma_idesc_f16_m256_mn(uint32_t n) {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((256u >> 4) << 24);
@@ -53,6 +60,8 @@ wgrad3x3_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
+  const uint32_t kWpChunk = wp_chunk_bytes(p.th), kWpABytes = 2u * kWpChunk, kWpSlab = wp_slab_bytes(p.th);
+  const uint32_t kWpStageBytes = wp_stage_bytes(p.th);
   const uint32_t bar_base = smem_base + stages * kWpStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -99,11 +108,11 @@ wgrad3x3_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       const int b = (int)(kb / tiles);
       const int rr = (int)(kb - (long long)b * tiles);
       const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
-      const int x0 = tx * 8, y0 = ty * 16;
+      const int x0 = tx * 8, y0 = ty * p.th;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sa = smem_base + stage * kWpStageBytes;
       if (elect_one()) {
-        if (rank == 0) mbar_expect_tx(full_bar(stage), (uint32_t)(2 * (kWpABytes + kWpBBytes)));
+        if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (kWpABytes + wp_slab_tx(p.th)));
         const uint32_t bar = mapa_cluster(full_bar(stage), 0);
 #pragma unroll
         for (int m = 0; m < 2; ++m)
@@ -124,10 +133,11 @@ wgrad3x3_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         const uint32_t sa = smem_base + stage * kWpStageBytes;
         const uint32_t sb = sa + kWpABytes;
         if (elect_one()) {
+          const int n_j = p.th >> 1;
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {       // 16 pixels = 2 image rows of the tile per MMA
+#pragma unroll 4
+            for (int j = 0; j < n_j; ++j) {     // 16 pixels = 2 image rows of the tile per MMA
               const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)j * 2048u, kWpChunk);
               const uint64_t bdesc =
                   umma_desc_mn_sw128_sbo(sb + (uint32_t)(2 * j) * 1280u + (uint32_t)s * 128u, kWpSlab, 1280u);
@@ -181,8 +191,25 @@ int try_wgrad3x3_pair(const void* dy, const void* x, float* dw, int B, int H, in
   WgradPairParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;
+  // rows per k-block: the even height <= 26 that wastes the fewest rows of the map (ties: the taller tile, fewer
+  // k-blocks), while at least two stages fit; DREAMB200_WGRAD_TH pins it (A/B; 16 = round 1)
+  int th = 16;
+  {
+    const char* e_th = getenv("DREAMB200_WGRAD_TH");
+    int pinned = e_th ? atoi(e_th) : 0;
+    if (pinned >= 2 && pinned <= 26 && pinned % 2 == 0) {
+      th = pinned;
+    } else {
+      long long best = -1;
+      for (int t = 4; t <= 26; t += 2) {
+        const long long rows = (long long)((H + t - 1) / t) * t;
+        if (best < 0 || rows < best || (rows == best && t > th)) { best = rows; th = t; }
+      }
+    }
+  }
+  p.th = th;
   p.tiles_x = (W + 7) / 8;
-  p.tiles_y = (H + 15) / 16;
+  p.tiles_y = (H + th - 1) / th;
   p.co_pairs = Cout_pad / 256;
   p.ci_tiles = Cin_pad / kWpN;
   p.kblocks_total = (long long)B * p.tiles_x * p.tiles_y;
@@ -197,21 +224,21 @@ int try_wgrad3x3_pair(const void* dy, const void* x, float* dw, int B, int H, in
   CUtensorMap tmDY, tmX;
   const uint32_t es[4] = {1, 1, 1, 1};
   {
-    const uint32_t box[4] = {64, 8, 16, 1};
+    const uint32_t box[4] = {64, 8, (uint32_t)th, 1};
     uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cout_pad * 2, (uint64_t)W * Cout_pad * 2, (uint64_t)H * W * Cout_pad * 2};
     if (make_tensor_map_f16(&tmDY, dy, 4, dims, str, box, es, "wgrad pair dY")) return -1;
   }
   {
-    const uint32_t box[4] = {64, 10, 16, 1};
+    const uint32_t box[4] = {64, 10, (uint32_t)th, 1};
     uint64_t dims[4] = {(uint64_t)Cin_pad, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin_pad * 2, (uint64_t)W * Cin_pad * 2, (uint64_t)H * W * Cin_pad * 2};
     if (make_tensor_map_f16(&tmX, x, 4, dims, str, box, es, "wgrad pair X")) return -1;
   }
-  int stages = (232448 - 1024 - 512) / kWpStageBytes;
+  int stages = (232448 - 1024 - 512) / (int)wp_stage_bytes(th);
   if (stages > 6) stages = 6;
   p.stages = stages;
-  const int smem_bytes = 1024 + stages * kWpStageBytes + 512;
+  const int smem_bytes = 1024 + stages * (int)wp_stage_bytes(th) + 512;
   static bool attr_set = false;
   if (!attr_set) {
     DB_CHECK_CUDA(cudaFuncSetAttribute(wgrad3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

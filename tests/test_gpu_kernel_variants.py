@@ -234,7 +234,8 @@ def test_conv_pair_kernel_is_bit_identical_to_single_cta(name, built_lib):
 
 
 @pytest.mark.parametrize("B,H,W,Ci,Co", [(3, 25, 25, 128, 256), (2, 50, 37, 256, 256), (2, 13, 13, 512, 512),
-                                         (2, 1, 9, 256, 512)])
+                                         (2, 1, 9, 256, 512), (1, 100, 100, 128, 256), (2, 26, 25, 128, 256),
+                                         (1, 27, 16, 128, 256)])
 def test_wgrad_pair_kernel_matches_single_cta_and_autograd(B, H, W, Ci, Co, built_lib):
     from dream_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -253,6 +254,12 @@ def test_wgrad_pair_kernel_matches_single_cta_and_autograd(B, H, W, Ci, Co, buil
     torch.nn.functional.conv2d(xr, wz, padding=1).backward(dy.permute(0, 3, 1, 2).float())
     ref = wz.grad.permute(2, 3, 0, 1).reshape(9, Co, Ci)
     assert (pair - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    # the pair kernel picks its tile height from the map (10 rows at 50x50, 20 at 100x100, 26 at 25x25 ...): every
+    # pinned height must give the same sums
+    for th in ("16", "6", "22"):
+        with env(DREAMB200_WGRAD3_2SM="1", DREAMB200_WGRAD_TH=th):
+            pinned = ops.wgrad(dy, x, ops.TAPS_3x3)
+        assert (single - pinned).abs().max().item() <= 1e-5 * scale, th
 
 
 def test_cuda_graph_inference_is_bit_identical_to_eager_and_follows_the_weights(built_lib):

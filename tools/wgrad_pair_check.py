@@ -72,7 +72,7 @@ def main():
         if "error" not in got["0"] and "error" not in got["1"]:
             a = torch.load("/tmp/wgp_%s_0.pt" % name); b = torch.load("/tmp/wgp_%s_1.pt" % name)
             rec["rel_diff"] = float((a - b).abs().max() / a.abs().max())
-            rec["ok"] = rec["rel_diff"] <= 1e-5
+            rec["ok"] = rec["rel_diff"] <= (5e-5 if CASES[name][5] else 1e-5)   # B = 128: ~1e6-term fp32 sums, different k-blocking
         ok_all = ok_all and rec.get("ok", False)
         print(json.dumps(rec), flush=True)
     print("ALL OK" if ok_all else "MISMATCH / ERROR")
