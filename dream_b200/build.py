@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdreamb200.so")
-SOURCES = ["conv_tc.cu", "conv_rs.cu", "conv_rs2.cu", "conv_tc2.cu", "first_conv.cu", "aux_kernels.cu", "peaks.cu", "train_kernels.cu", "wgrad_pair.cu", "input_kernels.cu", "wgrad_first.cu"]
+SOURCES = ["conv_tc.cu", "conv_rs.cu", "conv_rs2.cu", "conv_rs3.cu", "conv_tc2.cu", "first_conv.cu", "aux_kernels.cu", "peaks.cu", "train_kernels.cu", "wgrad_pair.cu", "input_kernels.cu", "wgrad_first.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -110,6 +110,7 @@ constexpr uint32_t kGateSlotBytes = 128 * 128;
 // vgg networks): those options compile away -- the epilogue of the 64-channel layers paces the kernel (two warps
 // per scheduler, one dependent chain per tile), so every runtime test on the chain counts.
 // GRING: the ReLU gate always arrives through a GateRing (`gr`), the per-thread gate loads compile away.
+// hand_back = false: the caller has more columns of this accumulator stage to drain (conv_rs3.cu) and returns it itself.
 template <int BLOCK_N, int SPLIT = 1, bool CLUSTER_ARRIVE = false, bool PLAIN = false, bool GRING = false>
 __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                    uint32_t t_row, uint32_t smem_out, uint32_t smem_pool,
@@ -118,7 +119,8 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
                                                    int lane, int epi_tid, uint32_t& chunk_ctr, int hsel = 0,
                                                    float* csum = nullptr, const float* breg = nullptr,
                                                    ResRing* rr = nullptr, uint32_t tfull_addr = 0u,
-                                                   uint32_t tfull_phase = 0u, GateRing* gr = nullptr) {
+                                                   uint32_t tfull_phase = 0u, GateRing* gr = nullptr,
+                                                   bool hand_back = true) {
   constexpr int kEpiThreads = 128 * SPLIT;
   constexpr int kRegs = 32 / SPLIT;                    // packed fp16 pairs per thread per chunk
   if (p.n_tiles > 1) {
@@ -234,7 +236,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
           for (int i = 0; i < 4; ++i) packed[hh][i] = pack_h2(q[2 * i], q[2 * i + 1]);
         }
-        if (c == BLOCK_N / 64 - 1) {
+        if (c == BLOCK_N / 64 - 1 && hand_back) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -458,7 +460,7 @@ __device__ __forceinline__ void epilogue_nhwc_tile(const ConvParams& p, const CU
 #pragma unroll
       for (int i = 0; i < 16; ++i) hv[hh * 16 + i] = pack_h2(f[2 * i], f[2 * i + 1]);
     }
-    if (c == BLOCK_N / 64 - 1) {
+    if (c == BLOCK_N / 64 - 1 && hand_back) {
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp right away
       tc_fence_before();
       __syncwarp();

@@ -308,6 +308,7 @@ int try_conv_tc2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_tc
 int try_conv_tc2_phases(const dreamb200_conv_desc* descs, int n_phases, cudaStream_t stream);
 int try_conv_rs(const dreamb200_conv_desc* d, cudaStream_t stream);   // conv_rs.cu
 int try_conv_rs2(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_rs2.cu
+int try_conv_rs3(const dreamb200_conv_desc* d, cudaStream_t stream);  // conv_rs3.cu
 
 template <int BLOCK_N, int OUT_MODE>
 static int launch(const dreamb200_conv_desc* d, cudaStream_t stream, int num_sms) {
@@ -461,6 +462,8 @@ extern "C" int dreamb200_conv2d_fwd(const dreamb200_conv_desc* d, void* stream_v
              "conv: output strides must be multiples of 16 bytes");
   {
     int r = try_conv_tc2(d, stream);           // CTA-pair kernel for the wide layers (DREAMB200_TC2=0 switches it off)
+    if (r != 0) return r > 0 ? 0 : r;
+    r = try_conv_rs3(d, stream);               // two-output-rows slab kernel for 64 -> 64 channels (DREAMB200_RS3)
     if (r != 0) return r > 0 ? 0 : r;
     r = try_conv_rs2(d, stream);               // CTA-pair slab kernel (DREAMB200_RS2 bit mask)
     if (r != 0) return r > 0 ? 0 : r;

@@ -456,13 +456,11 @@ class DreamNetwork:
             if optimizer_type == "adam":
                 assert "learning_rate" in cfg["optimizer"], \
                     'Required key "learning_rate" in dictionary "optimizer" is missing to use the Adam optimizer.'
-                network_parameters = list(network_parameters)
-                # torch's single-kernel ("fused") Adam: the same update as the default multi-tensor implementation the
-                # reference gets (dream/network.py:380-395) in one pass over the 22 M parameters instead of ~10
-                fused = (os.environ.get("DREAMB200_FUSED_ADAM", "1") != "0" and len(network_parameters) > 0 and
-                         all(p.is_cuda and p.is_floating_point() for p in network_parameters))
-                self.optimizer = torch.optim.Adam(network_parameters, lr=cfg["optimizer"]["learning_rate"],
-                                                  **({"fused": True} if fused else {}))
+                # (torch's default multi-tensor Adam, like the reference.  The single-kernel `fused=True` variant was tried:
+                #  it updates the parameters without bumping their version counters, which the packed-weight cache of
+                #  dream_b200.models keys on -- the next forward ran on stale fp16 weights; 0.25 ms per step is not worth
+                #  a second invalidation path.)
+                self.optimizer = torch.optim.Adam(network_parameters, lr=cfg["optimizer"]["learning_rate"])
             elif optimizer_type == "sgd":
                 assert "learning_rate" in cfg["optimizer"], \
                     'Required key "learning_rate" in dictionary "optimizer" is missing to use the SGD optimizer.'

@@ -121,6 +121,14 @@ def conv_taps(x, w, bias, taps, Ho, Wo, stride=1, relu=False, residual=None, y=N
                    ((mode & 8) if Cin == 64 else (mode & 2)) if Cout_pad == 128 else 0
             if want and pair_util >= float(os.environ.get("DREAMB200_RS2_MIN_UTIL", 0.7)):
                 fam = "conv_rs2"
+        plain = (residual is None and residual_f32 is None and y_f32 is None and gate is None and out_scale is None and
+                 colsum is None and absmax is None)
+        if (head_cout is None and T == 9 and stride == 1 and tuple(taps) == tuple(TAPS_3x3) and Cout_pad == 64 and
+                Cin == 64 and Ho >= 32 and plain and pool != "both"):      # mirror of try_conv_rs3 (conv_rs3.cu)
+            mode3 = int(os.environ.get("DREAMB200_RS3", "3"))
+            util3 = Ho * Wo / (((Wo + 15) // 16) * ((Ho + 31) // 32) * 512.0)
+            if (mode3 & (1 if pool else 2)) and util3 >= 0.65:
+                fam = "conv_rs3"
         tag = "%s<%d> T%d Cin%d Cout%d %dx%d s%d" % (fam, block_n, T, Cin, Cout_pad, Ho, Wo, stride)
         PROFILE.append((tag + (" +pool" if pool else ""), 2.0 * B * Ho * Wo * Cout_pad * Cin * T, e0, e1))
     else:

@@ -233,6 +233,40 @@ def test_conv_pair_kernel_is_bit_identical_to_single_cta(name, built_lib):
     assert (got.float() - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 48), (1, 100, 100), (3, 37, 53), (2, 33, 41), (1, 400, 400), (2, 32, 8),
+                                   (1, 96, 17)])
+@pytest.mark.parametrize("pool", [None, "only"])
+def test_two_row_slab_kernel_is_bit_identical_to_the_pair_kernel(B, H, W, pool, built_lib):
+    """conv_rs3 (one accumulator row = two vertically adjacent output pixels, 64 -> 64 channels) against conv_rs2 /
+    conv_rs on the same layer: every output receives the same partial products in the same order -> identical bits,
+    with and without the fused 2x2 max pool, on full, ragged and odd-sized maps; and both are the convolution."""
+    from dream_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + W)
+    x = (torch.randn((B, H, W, 64), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((64, 64, 3, 3), device="cuda", generator=g) * (1.0 / (64 * 9) ** 0.5)
+    bias = torch.randn((64,), device="cuda", generator=g) * 0.1
+    rs = [(r, s) for r in range(3) for s in range(3)]
+    wp, bp = ops.pack_conv_weight(w, rs), ops.pad_bias(bias, 64, "cuda")
+
+    def run():
+        y = ops.conv_taps(x, wp, bp, ops.TAPS_3x3, H, W, relu=True, pool=pool)
+        outs = [t for t in (y if isinstance(y, tuple) else (y,)) if t is not None]
+        torch.cuda.synchronize()
+        return outs
+
+    with env(DREAMB200_RS3="0"):
+        old = run()
+    with env(DREAMB200_RS3="3"):
+        new = run()
+    assert len(old) == len(new) == 1
+    assert torch.equal(old[0], new[0])
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), bias, padding=1))
+    if pool is not None:
+        ref = torch.nn.functional.max_pool2d(ref, 2)
+    assert (new[0].float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("B,H,W,Ci,Co", [(3, 25, 25, 128, 256), (2, 50, 37, 256, 256), (2, 13, 13, 512, 512),
                                          (2, 1, 9, 256, 512), (1, 100, 100, 128, 256), (2, 26, 25, 128, 256),
                                          (1, 27, 16, 128, 256)])
