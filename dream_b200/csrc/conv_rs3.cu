@@ -25,7 +25,9 @@
 // The pair is two horizontally adjacent 8-pixel columns of 32 output rows; slab = 34 image rows x 10 pixels x 128 B.
 // 2x2 max pooling pairs exactly the two halves of an accumulator row (vertical, in the thread) and lanes l, l^1
 // (horizontal): the pooled epilogue is 32 fmax + 16 shuffles per thread.  PLAIN launches only (inference and the
-// training forward of the un-pooled layers); everything else stays on conv_rs2.
+// training forward of the un-pooled layers); everything else stays on conv_rs2.  (A gated data-gradient variant was
+// built and measured in round 2: with the 68 KB of weights only two 43 KB slabs and two gate chunks fit, and it ran
+// 2.14 ms against conv_rs2's 2.03 ms on the 400x400 layer -- removed again.)
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "dreamb200.h"

@@ -36,6 +36,7 @@ double conv_choose_tile(int Wo, int Ho, int in_stride, bool even, int* tw_out, i
 
 constexpr int kT2Split = 2;
 constexpr int kT2Threads = 64 + 128 * kT2Split;
+constexpr int kT2ThreadsRes = kT2Threads + 32;            // + the residual-ring TMA warp (launches with res_slots > 0)
 constexpr int kT2MaxPhases = 4;
 constexpr int kNotEligible = -100;
 
@@ -46,7 +47,7 @@ struct PhaseMaps {
 };
 
 template <int kT2N, bool PLAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2ThreadsRes, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ PhaseMaps pm,
                 const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ ConvParams p) {
@@ -127,8 +128,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== TMA producer (both CTAs; bytes are counted on the leader's barriers) =====================
     int stage = 0;
     uint32_t phase = 0;
-    int rs = 0;
-    uint32_t rph = 0;
     for (int q = pair; q < p.total_tiles; q += n_pairs) {
       int sp, n, tx, ty, b;                                   // sp = sub-pixel phase of a phase group (0 otherwise)
       decode(q, sp, n, tx, ty, b);
@@ -146,22 +145,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_load_3d_2sm(sa + kABytes, tmB, bar, kc * 64, n * kT2N + (int)rank * (kT2N / 2), tap);
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
-        }
-      }
-      if (res_slots > 0) {
-        // The identity stream of a ResNet expansion layer: 4 bytes read per output element against 2 * Cin MACs.
-        // Read by the epilogue threads themselves it was latency-bound -- 32 KB in flight per SM, 2.8 TB/s over the
-        // chip.  Here this tile's residual (own CTA's M-tile, own barriers: no pair traffic) is fetched by TMA one
-        // 64-column chunk per slot, a whole tile (res_slots x 32 KB) ahead of the epilogue.
-        for (int c = 0; c < kT2N / 64; ++c) {
-          mbar_wait(rempty_bar(rs), rph ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(rfull_bar(rs), (uint32_t)(2 * p.tw * p.th * 128));
-            const uint32_t dst = smem_res + (uint32_t)rs * kResSlotBytes;
-            tma_load_4d(dst, &tmR, rfull_bar(rs), n * kT2N + c * 64, tx * p.tw, ty * p.th, b);
-            tma_load_4d(dst + kResSubBytes, &tmR, rfull_bar(rs), n * kT2N + c * 64 + 32, tx * p.tw, ty * p.th, b);
-          }
-          if (++rs == res_slots) { rs = 0; rph ^= 1u; }
         }
       }
     }
@@ -194,6 +177,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         as ^= 1;
         if (as == 0) aphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ===================== fp32 residual ring (launches with res_slots > 0 carry this 11th warp) =====================
+    // The identity stream of a ResNet expansion layer: 4 bytes read per output element against 2 * Cin MACs.
+    // Read by the epilogue threads themselves it was latency-bound -- 32 KB in flight per SM, 2.8 TB/s over the
+    // chip.  Here each tile's residual (own CTA's M-tile, own barriers: no pair traffic) is fetched by TMA one
+    // 64-column chunk per slot, as far ahead of the epilogue as the ring has free slots.
+    // A warp of its own: when the operand producer issued these loads between the operand loads of two tiles, the ring
+    // ran dry while that warp sat in the (single-stage, hence serial) operand chain of the next tile, and the operand
+    // chain stalled while it waited for ring slots -- epilogue and MMA phases ran back to back instead of overlapped
+    // (11 us per tile for 320 KB of traffic, 4.0 TB/s of DRAM traffic under ncu).
+    if (res_slots > 0) {
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int q = pair; q < p.total_tiles; q += n_pairs) {
+        int sp, n, tx, ty, b;
+        decode(q, sp, n, tx, ty, b);
+        for (int c = 0; c < kT2N / 64; ++c) {
+          mbar_wait(rempty_bar(rs), rph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(rfull_bar(rs), (uint32_t)(2 * p.tw * p.th * 128));
+            const uint32_t dst = smem_res + (uint32_t)rs * kResSlotBytes;
+            tma_load_4d(dst, &tmR, rfull_bar(rs), n * kT2N + c * 64, tx * p.tw, ty * p.th, b);
+            tma_load_4d(dst + kResSubBytes, &tmR, rfull_bar(rs), n * kT2N + c * 64 + 32, tx * p.tw, ty * p.th, b);
+          }
+          if (++rs == res_slots) { rs = 0; rph ^= 1u; }
+        }
       }
     }
     __syncwarp();
@@ -303,11 +315,21 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
     // with an fp32 output too (every expansion layer but a stage's last) the result leaves through the SAME slots: two
     // of them are then busy with pending stores, so the ring grows by one slot and the operand pipeline -- idle 90 % of
     // the time in these HBM-bound layers -- shrinks to a single stage
+    // ... unless the layer's K loop is long (512 -> 2048: 8 k-blocks per tile): a single stage makes the operand loads
+    // of a tile strictly serial (~1 us each), which then outlasts the epilogue (DREAMB200_RES_INPLACE_MAXKB, default 4)
     const char* e2 = getenv("DREAMB200_RES_INPLACE");
+    const char* e3 = getenv("DREAMB200_RES_INPLACE_MAXKB");
+    const int max_kb = e3 ? atoi(e3) : 4;
     if (res_slots > 0 && d->y_f32 != nullptr && ((uintptr_t)d->y_f32 & 15) == 0 && !(e2 && e2[0] == '0') &&
+        d->taps * (d->Cin / 64) <= max_kb &&
         232448 - 1024 - out_bytes - 512 - kT2N * 4 - (res_slots + 1) * (int)kResSlotBytes >= kT2StageBytes) {
       res_slots += 1;
       p.res_inplace = 1;
+      // Ring depth.  Five slots (two draining, one in work, two ahead) left room for ONE operand stage, which makes a
+      // tile's k-block loads strictly serial; four slots (one less ahead) and two stages measured better: resnet-H
+      // expansions 2.10 -> 1.94 ms per step (DREAMB200_RES_INPLACE_SLOTS=5 restores the deeper ring)
+      const char* e4 = getenv("DREAMB200_RES_INPLACE_SLOTS");
+      res_slots = (e4 && atoi(e4) >= 3 && atoi(e4) <= res_slots) ? atoi(e4) : res_slots - 1;
     }
   }
   p.res_slots = res_slots;
@@ -375,7 +397,7 @@ static int launch_tc2(const dreamb200_conv_desc* descs, int n_phases, cudaStream
   }
   const int sms = device_sm_count() & ~1;
   const int grid = 2 * p.total_tiles < sms ? 2 * p.total_tiles : sms;
-  kern<<<grid, kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, tmR, tmY, p);
+  kern<<<grid, res_slots > 0 ? kT2ThreadsRes : kT2Threads, smem_bytes, stream>>>(tmA, pm, tmP, tmR, tmY, p);
   DB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
