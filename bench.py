@@ -417,7 +417,7 @@ def measure(args, workload, rank, world, local, dev, primary=True):
     # e2e crosses PCIe and the host: on shared boxes single runs scatter (observed 4.6k .. 7.5k img/s for the same
     # build), so K steps are timed three times and the median run is reported
     e2e_runs = sorted(timed(run_e2e, args.steps, args.warmup if i == 0 else 1, whole=True)[0]
-                      for i in range(3 if primary else 1))
+                      for i in range(3))
     ms_e2e = e2e_runs[len(e2e_runs) // 2]
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 

@@ -23,8 +23,18 @@ if target == "conv256":            # layer_0_3_down.12/.14: 256->256 @100x100 (c
     conv_case(100, 100, 256, 256)
 elif target == "conv512":          # layer_0_4_down.21..25: 512->512 @50x50
     conv_case(50, 50, 512, 512)
-elif target == "rs64":             # layer_0_1_down.2: 64->64 @400x400 + fused pool (conv_rs_kernel<64,true>)
+elif target == "rs64":             # layer_0_1_down.2: 64->64 @400x400 + fused pool (conv_rs3_kernel<true> since round 2)
     conv_case(400, 400, 64, 64, pool="only")
+elif target == "dgrad64":         # data gradient of layer_0_1_down.2 (64 -> 64 @400x400): ReLU gate staged by TMA, re-scaling,
+    # bias-gradient column sums, running max (conv_rs2_kernel<64, ., false> with the gate ring)
+    dy = (torch.randn((B, 400, 400, 64), device="cuda", generator=g) * 0.5).half()
+    w = torch.randn((64, 64, 3, 3), device="cuda", generator=g) * (1.0 / (64 * 9) ** 0.5)
+    wp = ops.pack_conv_weight(w, [(r, s) for r in range(3) for s in range(3)])
+    gate = torch.relu(torch.randn((B, 400, 400, 64), device="cuda", generator=g)).half()
+    scale = torch.full((1,), 2.0, device="cuda")
+    for _ in range(3):
+        amax = torch.zeros((1,), device="cuda"); col = torch.zeros((64,), device="cuda")
+        ops.conv_taps(dy, wp, None, ops.TAPS_3x3, 400, 400, gate=gate, out_scale=scale, colsum=col, absmax=amax)
 elif target == "rs128":            # layer_0_2_down.7: 128->128 @200x200 + fused pool (conv_rs_kernel<128,false>)
     conv_case(200, 200, 128, 128, pool="only")
 elif target == "first":            # layer_0_1_down.0 fused with the input pack (first_conv_kernel)
@@ -36,6 +46,11 @@ elif target == "first":            # layer_0_1_down.0 fused with the input pack 
 elif target == "wgrad256":
     x = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
     dy = (torch.randn((B, 100, 100, 256), device="cuda", generator=g) * 0.5).half()
+    for _ in range(3):
+        ops.wgrad(dy, x, ops.TAPS_3x3)
+elif target == "wgrad512":         # 512 -> 512 @50x50: wgrad3x3_pair_kernel with 10-row tiles (round 2: 1.23 -> 1.03 ms)
+    x = (torch.randn((B, 50, 50, 512), device="cuda", generator=g) * 0.5).half()
+    dy = (torch.randn((B, 50, 50, 512), device="cuda", generator=g) * 0.5).half()
     for _ in range(3):
         ops.wgrad(dy, x, ops.TAPS_3x3)
 elif target == "expand":           # resnet layer3 conv3: 1x1 256 -> 1024 @25x25 + fp32 identity in / out (conv_tc2, residual ring)
