@@ -217,6 +217,15 @@ class _PlanModule(nn.Module):
             key.append((t.data_ptr(), t._version))
         return tuple(key)
 
+    def invalidate_packed_weights(self):
+        """Forget the packed fp16 weights.  They are rebuilt whenever a parameter's or buffer's version counter (or
+        storage) changes -- every in-place torch op bumps it.  Updates that bypass the counters do not: torch's
+        single-kernel optimizers (`torch.optim.Adam(..., fused=True)`) and writes through raw pointers; call this
+        after such an update (DreamNetwork.train uses the default multi-tensor optimizers and needs nothing)."""
+        self._plan = self._plan_key = None
+        if hasattr(self, "_pp"):
+            self._pp = None
+
     def plan(self):
         key = self._version_key()
         if self._plan is None or key != self._plan_key:

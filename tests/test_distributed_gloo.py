@@ -131,3 +131,25 @@ def test_single_process_is_a_no_op():
     assert torch.equal(g, m.weight.grad)
     assert D.shard_indices(5) == [0, 1, 2, 3, 4]
     assert D.gather_rows([1, 2], 2) == [1, 2]
+
+
+def test_grad_reducer_bucket_layout_keeps_the_last_bucket_small():
+    """Bucket layout only (no process group needed): reverse parameter order, ~bucket_bytes per bucket, and the trailing
+    parameters -- the first layers, whose gradients are the last to be produced -- in a small bucket of their own, so
+    that the one all-reduce that cannot hide behind backward is a short one."""
+    from dream_b200 import distributed as D
+    sizes = [100, 2000, 6000, 9000, 9000, 500]                       # parameters in forward order, numels
+    model = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(n)) for n in sizes])
+    r = D.GradReducer(model, bucket_bytes=10000 * 4, tail_bytes=2500 * 4)
+    assert r.flat.numel() == sum(sizes)
+    # reverse order, a bucket closes once it holds >= 10000 elements: 500 + 9000 + 9000 | 6000 (closed early by the tail
+    # cut) | 2000 + 100 = the tail (<= 2500 elements)
+    assert [b[1] - b[0] for b in r.buckets] == [18500, 6000, 2100]
+    assert [b[2] for b in r.buckets] == [3, 1, 2]
+    params = list(model)
+    assert r.bucket_of[id(params[0])] == r.bucket_of[id(params[1])] == 2
+    assert r.views[id(params[5])].data_ptr() == r.flat.data_ptr()    # the last parameter's gradient comes first
+    # a single huge first parameter cannot be split: it simply is the tail
+    model2 = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(n)) for n in (50000, 10, 10)])
+    r2 = D.GradReducer(model2, bucket_bytes=10000 * 4, tail_bytes=2500 * 4)
+    assert sum(b[1] - b[0] for b in r2.buckets) == 50020 and r2.buckets[-1][1] == 50020

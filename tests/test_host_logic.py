@@ -201,3 +201,17 @@ def test_pretrained_trunks_load_from_a_local_checkpoint_or_warn(tmp_path, monkey
     assert float(sd["layer_0_3_down.12.weight"].mean()) == 12.0 and float(sd["layer_0_5_down.34.bias"].mean()) == 34.5
     assert float(sd["layer_0_1_down.2.weight"].mean()) == 2.0
     assert float(sd["layer_0_1_down.0.weight"].abs().max()) < 1.0          # the fresh first conv keeps its own init
+
+
+def test_invalidate_packed_weights_forgets_the_plan():
+    """Updates that bypass torch's version counters (fused optimizers, raw pointer writes) need an explicit
+    invalidation of the packed fp16 weights."""
+    from dream_b200 import models
+    net = models.DreamHourglass(7, internalize_spatial_softmax=False)
+    net._plan, net._plan_key = {"stale": True}, ("key",)
+    net.invalidate_packed_weights()
+    assert net._plan is None and net._plan_key is None
+    key0 = net._version_key()
+    with torch.no_grad():
+        next(net.parameters()).mul_(1.0)             # any in-place torch op bumps the counter the cache keys on
+    assert net._version_key() != key0
