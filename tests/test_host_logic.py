@@ -215,3 +215,23 @@ def test_invalidate_packed_weights_forgets_the_plan():
     with torch.no_grad():
         next(net.parameters()).mul_(1.0)             # any in-place torch op bumps the counter the cache keys on
     assert net._version_key() != key0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, on the host cores) prints ONE JSON line
+    with the CUDA arm's metric / unit / config plus impl, cpu_baseline and an e2e block without copies."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "images/sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert set(d["config"]) == {"workload", "parallelism", "l2"} and "batch 128/GPU, 400x400" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
