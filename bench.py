@@ -148,6 +148,24 @@ def cpu_baseline_sample(n_images, threads=None, keep=None):
     return n_images / (t_fwd + t_peaks), t_fwd, t_peaks, torch.get_num_threads()
 
 
+def cpu_single_frame_ms(reps=7, warmup=2):
+    """BASELINE.json configs[0]: one 400x400 frame, CPU forward of the reference path (oracle port),
+    fp32, no_grad; median of `reps` after `warmup` runs, all host threads torch currently uses."""
+    import torch
+    from oracle import ref_models
+    sd = synthetic_vgg_q_state()
+    x = oracle_frames(1)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            ref_models.vgg_forward(sd, x)
+            if i >= warmup:
+                ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def parity_line(model, xs0, ref, offset):
     """Parity evidence AT the benchmarked shape: the oracle's frames ride in the first slots of a full B=128 batch
     through the CUDA path (same synthetic weights on both arms); belief maps are compared with the oracle's, the
@@ -547,7 +565,9 @@ def measure(args, workload, rank, world, local, dev, primary=True):
         parity = parity_line(model, xs[0], ref_out, offset)
         cpu = {"value": r, "unit": "images/s", "cores": thr, "kind": "port",
                "sample": "8 frames 400x400: oracle port of dream/models.py forward (%.2f s) + image_proc peaks (%.2f s)"
-                         % (tf, tp)}
+                         % (tf, tp),
+               # BASELINE.json configs[0]: ONE 400x400 frame through the reference's CPU forward, median of 7 after 2 warm-ups
+               "single_frame_forward_ms": cpu_single_frame_ms()}
 
     if rank == 0:
         line = {
