@@ -16,6 +16,8 @@
 //     empty / accumulator-full barriers of BOTH CTAs;
 //   * each CTA's epilogue drains its own TMEM half and hands the accumulator stage back with a cluster-scope
 //     arrive on the leader's barrier (count = both CTAs' epilogue warps).
+// Warps: 0 = TMA producer (slabs, weights), 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two per TMEM lane quarter),
+// 10 = ReLU-gate TMA ring, present only in gated data-gradient launches (kR2ThreadsGate threads, see below).
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "dreamb200.h"

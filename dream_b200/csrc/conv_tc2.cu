@@ -18,6 +18,8 @@
 // output-channel tile n); TMA loads count their bytes on the LEADER's full barrier; the leader's elected lane issues
 // tcgen05.mma.cta_group::2 (M = 256, N = 256); tcgen05.commit multicast arrives on both CTAs' empty / accumulator-full
 // barriers; each CTA drains its own TMEM half and returns the stage with an arrive on the leader's barrier.
+// Warps: 0 = TMA producer (operands), 1 = MMA issuer + TMEM owner, 2..9 = epilogue, 10 = fp32 residual ring (only in
+// launches with res_slots > 0: the ResNet expansion layers).
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "dreamb200.h"
