@@ -235,3 +235,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert set(d["config"]) == {"workload", "parallelism", "l2"} and "batch 128/GPU, 400x400" in d["config"]["workload"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_two_row_accumulator_decomposition_is_the_convolution():
+    """Executable statement of conv_rs3.cu's scheme: accumulator row (x, j) holds output rows 2j (first
+    half of the columns) and 2j + 1 (second half); for input-row offset t = 0..3 and column tap s the A operand is the
+    input pixel (2j - 1 + t, x - 1 + s) and the B operand is W[0,s] (t = 0, first half), [W[1,s] | W[0,s]] (t = 1),
+    [W[2,s] | W[1,s]] (t = 2), W[2,s] (t = 3, second half).  Summed over (s, t) this is the 3x3 'same' convolution."""
+    rng = np.random.default_rng(0)
+    H, W, Ci, Co = 10, 7, 5, 3                                   # H even here; the kernel clips odd maps with TMA
+    x = rng.standard_normal((H, W, Ci))
+    w = rng.standard_normal((Co, Ci, 3, 3))
+    xp = np.zeros((H + 2, W + 2, Ci)); xp[1:-1, 1:-1] = x         # zero padding = TMA out-of-bounds fill
+    acc = np.zeros((H // 2, W, 2 * Co))                           # [j, x, (row 2j | row 2j + 1)]
+    for s in range(3):
+        for t in range(4):
+            a = xp[t:t + H:2, s:s + W]                            # A[j, x] = input (2j - 1 + t, x - 1 + s), padded coords
+            if t <= 2:
+                acc[:, :, :Co] += a @ w[:, :, t, s].T             # output row 2j uses kernel row r = t
+            if t >= 1:
+                acc[:, :, Co:] += a @ w[:, :, t - 1, s].T         # output row 2j + 1 uses r = t - 1
+    got = np.empty((H, W, Co)); got[0::2] = acc[:, :, :Co]; got[1::2] = acc[:, :, Co:]
+    ref = np.zeros((H, W, Co))
+    for r in range(3):
+        for s in range(3):
+            ref += xp[r:r + H, s:s + W] @ w[:, :, r, s].T
+    assert np.allclose(got, ref, atol=1e-12)
